@@ -1,0 +1,672 @@
+// -*- C++ -*-
+// K5: boundary exchange between chunks -- fields (copy), currents (add) and particle migration.
+//
+// Reference: nix::Chunk::{pack,begin,probe,end,unpack}_bc_exchange (nix/chunk.hpp:392-543,
+// nix/chunk.cpp:310-395) with the policies XtensorHaloField3D / XtensorHaloCurrent3D /
+// XtensorHaloParticle3D (nix/xtensor_halo3d.hpp:18-129, 192-499).  There every one of the 26
+// neighbour relations is an MPI message, even between chunks of the same rank.  Here:
+//   * neighbours inside the arena need NO message: one gather kernel reads the neighbour's cells
+//     directly (field: interior margin -> ghost, nix/chunk.cpp:171-207; current: ghost -> += interior
+//     margin, nix/xtensor_halo3d.hpp:93-99,119-125), visiting the directions in the reference's
+//     unpack order (dirz, diry, dirx ascending) so the floating-point sum order is the same;
+//   * chunks owned by another rank are served through ONE contiguous send and ONE receive buffer
+//     per peer rank and mode; the caller moves send -> recv (NCCL / P2P) between begin and end.
+//     Messages inside a buffer are ordered by (sender chunk id, sender direction) on both sides.
+//   * particles leaving a chunk are appended straight behind the destination chunk's active
+//     particles (periodic wrap + cell key + histogram update included, i.e. post_unpack's work,
+//     nix/xtensor_halo3d.hpp:477-491), or into the peer's staging buffer as 64-byte records.
+#include "particle_common.cuh"
+
+#include <algorithm>
+#include <tuple>
+
+namespace picnix
+{
+
+namespace
+{
+
+constexpr int HALO_THREADS = 128;
+
+// extent of the halo region of direction code dcode (0,1,2 per axis) along one axis
+__host__ __device__ inline int region_len(const Geom& g, int axis, int dcode)
+{
+  return dcode == 1 ? (g.Ub[axis] - g.Lb[axis] + 1) : g.nb;
+}
+
+// first index of the interior-margin region ("send_bound" of the field halo)
+__host__ __device__ inline int margin_lo(const Geom& g, int axis, int dcode)
+{
+  return dcode == 2 ? g.Ub[axis] - g.nb + 1 : g.Lb[axis];
+}
+
+// first index of the ghost region ("recv_bound")
+__host__ __device__ inline int ghost_lo(const Geom& g, int axis, int dcode)
+{
+  return dcode == 0 ? g.Lb[axis] - g.nb : (dcode == 1 ? g.Lb[axis] : g.Ub[axis] + 1);
+}
+
+__host__ __device__ inline bool dir_active(const Geom& g, int dz, int dy, int dx)
+{
+  // ignorable dimensions only take part with direction 0 (nix/chunk.cpp:141-169)
+  if (dz == 1 && dy == 1 && dx == 1)
+    return false;
+  if (!g.has_dim[0] && dz != 1)
+    return false;
+  if (!g.has_dim[1] && dy != 1)
+    return false;
+  if (!g.has_dim[2] && dx != 1)
+    return false;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// field halo, local neighbours: every ghost cell pulls from the owning neighbour's interior
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HALO_THREADS) field_halo_local_kernel(Geom g, DevPtrs d)
+{
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)g.nchunk * g.Ng)
+    return;
+  int chunk = (int)(t / g.Ng);
+  int r     = (int)(t - (int64_t)chunk * g.Ng);
+  int idx[3];
+  idx[0] = r / (g.M[1] * g.M[2]);
+  r -= idx[0] * g.M[1] * g.M[2];
+  idx[1] = r / g.M[2];
+  idx[2] = r - idx[1] * g.M[2];
+
+  int dcode[3], src[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    if (!g.has_dim[a]) {
+      if (idx[a] != g.Lb[a])
+        return; // ghost planes of ignorable dimensions are never exchanged
+      dcode[a] = 1;
+      src[a]   = idx[a];
+    } else if (idx[a] < g.Lb[a]) {
+      dcode[a] = 0;
+      src[a]   = idx[a] + g.dims[a];
+    } else if (idx[a] > g.Ub[a]) {
+      dcode[a] = 2;
+      src[a]   = idx[a] - g.dims[a];
+    } else {
+      dcode[a] = 1;
+      src[a]   = idx[a];
+    }
+  }
+  if (dcode[0] == 1 && dcode[1] == 1 && dcode[2] == 1)
+    return;
+
+  int nb = d.nbr[chunk * NBSIZE + 9 * dcode[0] + 3 * dcode[1] + dcode[2]];
+  if (nb < 0)
+    return; // none, or remote (served from the receive buffer in halo_end)
+
+  int64_t s = (((int64_t)nb * g.M[0] + src[0]) * g.M[1] + src[1]) * g.M[2] + src[2];
+#pragma unroll
+  for (int k = 0; k < 6; k++)
+    d.uf[t * 6 + k] = d.uf[s * 6 + k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// current halo, local neighbours: every interior-margin cell adds the neighbours' ghost cells
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HALO_THREADS) current_halo_local_kernel(Geom g, DevPtrs d)
+{
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)g.nchunk * g.Ng)
+    return;
+  int chunk = (int)(t / g.Ng);
+  int r     = (int)(t - (int64_t)chunk * g.Ng);
+  int idx[3];
+  idx[0] = r / (g.M[1] * g.M[2]);
+  r -= idx[0] * g.M[1] * g.M[2];
+  idx[1] = r / g.M[2];
+  idx[2] = r - idx[1] * g.M[2];
+
+  // only interior cells receive; for each axis, which direction codes reach this cell
+  bool reach[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    if (idx[a] < g.Lb[a] || idx[a] > g.Ub[a])
+      return;
+    reach[a][0] = g.has_dim[a] && idx[a] < g.Lb[a] + g.nb;
+    reach[a][1] = true;
+    reach[a][2] = g.has_dim[a] && idx[a] > g.Ub[a] - g.nb;
+  }
+
+  double acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    acc[k] = d.uj[t * 4 + k];
+  bool touched = false;
+
+  for (int dz = 0; dz < 3; dz++) {
+    if (!reach[0][dz])
+      continue;
+    for (int dy = 0; dy < 3; dy++) {
+      if (!reach[1][dy])
+        continue;
+      for (int dx = 0; dx < 3; dx++) {
+        if (!reach[2][dx] || (dz == 1 && dy == 1 && dx == 1))
+          continue;
+        int nb = d.nbr[chunk * NBSIZE + 9 * dz + 3 * dy + dx];
+        if (nb < 0)
+          continue;
+        // the neighbour's ghost cell that overlaps this interior cell
+        int sz = idx[0] + (dz == 0 ? g.dims[0] : (dz == 2 ? -g.dims[0] : 0));
+        int sy = idx[1] + (dy == 0 ? g.dims[1] : (dy == 2 ? -g.dims[1] : 0));
+        int sx = idx[2] + (dx == 0 ? g.dims[2] : (dx == 2 ? -g.dims[2] : 0));
+        int64_t s = (((int64_t)nb * g.M[0] + sz) * g.M[1] + sy) * g.M[2] + sx;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          acc[k] += d.uj[s * 4 + k];
+        touched = true;
+      }
+    }
+  }
+  if (touched) {
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      d.uj[t * 4 + k] = acc[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// remote messages for the fixed-size modes.  desc[m] = (local chunk, direction code 0..26)
+//   pack  : EMF sends the interior margin, CUR sends the ghost region
+//   unpack: EMF stores into the ghost region, CUR adds into the interior margin
+// One block per message; the element order inside a message is (z, y, x, component) like the
+// reference's strided_view copy.
+// ---------------------------------------------------------------------------------------------
+template <int NCOMP, bool IS_CURRENT, bool IS_PACK>
+__global__ void __launch_bounds__(HALO_THREADS)
+remote_halo_kernel(Geom g, double* __restrict__ field, const int* __restrict__ desc,
+                   const int64_t* __restrict__ msg_off, double* __restrict__ buf)
+{
+  const int m     = blockIdx.x;
+  const int chunk = desc[2 * m + 0];
+  const int dir   = desc[2 * m + 1];
+  const int dc[3] = {dir / 9, (dir / 3) % 3, dir % 3};
+
+  int lo[3], len[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    len[a] = region_len(g, a, dc[a]);
+    // pack/EMF and unpack/CUR touch the interior margin; pack/CUR and unpack/EMF the ghosts
+    bool interior = (IS_PACK != IS_CURRENT);
+    lo[a]         = interior ? margin_lo(g, a, dc[a]) : ghost_lo(g, a, dc[a]);
+  }
+  const int n   = len[0] * len[1] * len[2] * NCOMP;
+  double*   msg = buf + msg_off[m];
+
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    int k    = e % NCOMP;
+    int cell = e / NCOMP;
+    int jx   = cell % len[2];
+    int jy   = (cell / len[2]) % len[1];
+    int jz   = cell / (len[2] * len[1]);
+    int64_t c =
+        (((int64_t)chunk * g.M[0] + lo[0] + jz) * g.M[1] + lo[1] + jy) * g.M[2] + lo[2] + jx;
+    if (IS_PACK) {
+      msg[e] = field[c * NCOMP + k];
+    } else if (IS_CURRENT) {
+      field[c * NCOMP + k] += msg[e];
+    } else {
+      field[c * NCOMP + k] = msg[e];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// particle migration
+// ---------------------------------------------------------------------------------------------
+struct MigrateTables {
+  const int* slot_peer;  // remote slot -> peer index
+  double**   psend;      // [npeer] staging buffers (records of 8 doubles)
+  int**      psend_cnt;  // [npeer] record counters
+  const int64_t* psend_cap; // [npeer] capacity in records
+  const int* nbid;       // [nchunk][27] global neighbour ids (for remote records)
+};
+
+// append one particle behind the active particles of (chunk, species); p = 7 components
+__device__ __forceinline__ void append_particle(const Geom& g, const DevPtrs& d, int chunk, int is,
+                                                double* p)
+{
+  const int seg  = chunk * g.Ns + is;
+  const int slot = atomicAdd(d.ntail + seg, 1);
+  const int ip   = d.np[seg] + slot;
+  if (ip >= d.seg_cap[seg]) {
+    atomicExch(d.errflag + 0, 1);
+    return;
+  }
+  // post_unpack: periodic wrap, then count in the receiving chunk's geometry
+  wrap_periodic(g, p[0], p[1], p[2]);
+  const int64_t i = d.seg_off[seg] + ip;
+#pragma unroll
+  for (int k = 0; k < NC; k++)
+    d.xu[k * d.pcap + i] = p[k];
+  const int key = cell_key(g, d.clim + chunk * 6, p[0], p[1], p[2]);
+  d.gindex[i]   = key;
+  atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, 1);
+}
+
+__global__ void __launch_bounds__(HALO_THREADS)
+migrate_kernel(Geom g, DevPtrs d, MigrateTables tab, int blocks_per_seg)
+{
+  const int seg   = blockIdx.x / blocks_per_seg;
+  const int b     = blockIdx.x - seg * blocks_per_seg;
+  const int ip    = b * blockDim.x + threadIdx.x;
+  if (ip >= d.np[seg])
+    return;
+  const int64_t i = d.seg_off[seg] + ip;
+  if (d.gindex[i] != g.Ng)
+    return; // still inside its chunk
+
+  const int chunk = seg / g.Ns;
+  const int is    = seg - chunk * g.Ns;
+  double    p[NC];
+#pragma unroll
+  for (int k = 0; k < NC; k++)
+    p[k] = d.xu[k * d.pcap + i];
+
+  const int dir = direction_code(g, d.clim + chunk * 6, p[0], p[1], p[2]);
+  if (dir == 13)
+    return;
+  const int nb = d.nbr[chunk * NBSIZE + dir];
+  if (nb >= 0) {
+    append_particle(g, d, nb, is, p);
+  } else if (nb <= NB_REMOTE_BASE) {
+    const int     slot = NB_REMOTE_BASE - nb;
+    const int     peer = tab.slot_peer[slot];
+    const int     rec  = atomicAdd(tab.psend_cnt[peer], 1);
+    if (rec >= tab.psend_cap[peer]) {
+      atomicExch(d.errflag + 1, 1);
+      return;
+    }
+    double* out = tab.psend[peer] + (int64_t)rec * 8;
+#pragma unroll
+    for (int k = 0; k < NC; k++)
+      out[k] = p[k];
+    // destination: global chunk id and species, packed into the eighth slot
+    int2 tag = make_int2(tab.nbid[chunk * NBSIZE + dir], is);
+    out[7]   = *reinterpret_cast<double*>(&tag);
+  }
+  // NB_NONE: open boundary, the particle is simply dropped by the sort (MPI_PROC_NULL send)
+}
+
+__global__ void __launch_bounds__(HALO_THREADS)
+unpack_particle_kernel(Geom g, DevPtrs d, const double* __restrict__ recv, int nrec,
+                       int chunk_begin)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrec)
+    return;
+  const double* in = recv + (int64_t)r * 8;
+  double        p[NC];
+#pragma unroll
+  for (int k = 0; k < NC; k++)
+    p[k] = in[k];
+  double tagbits = in[7];
+  int2   tag     = *reinterpret_cast<int2*>(&tagbits);
+  int    chunk   = tag.x - chunk_begin;
+  if (chunk < 0 || chunk >= g.nchunk || tag.y < 0 || tag.y >= g.Ns) {
+    atomicExch(d.errflag + 2, 1);
+    return;
+  }
+  append_particle(g, d, chunk, tag.y, p);
+}
+
+int64_t region_elems(const Geom& g, int dir, int ncomp)
+{
+  int dc[3] = {dir / 9, (dir / 3) % 3, dir % 3};
+  return (int64_t)region_len(g, 0, dc[0]) * region_len(g, 1, dc[1]) * region_len(g, 2, dc[2]) *
+         ncomp;
+}
+
+template <typename T>
+int upload_vector(picnix_arena* a, T** dptr, const std::vector<T>& host)
+{
+  PICNIX_CUDA(a, cudaMalloc((void**)dptr, std::max<size_t>(host.size(), 1) * sizeof(T)));
+  if (!host.empty())
+    PICNIX_CUDA(a, cudaMemcpy(*dptr, host.data(), host.size() * sizeof(T),
+                              cudaMemcpyHostToDevice));
+  return PICNIX_OK;
+}
+
+} // namespace
+
+// Neighbour codes + per-peer message plan.  Called once from arena_create.
+int build_comm_plan(picnix_arena* a)
+{
+  const Geom& g      = a->g;
+  const int   myrank = a->cfg.rank;
+
+  struct Msg {
+    int sender_id, sender_dir, chunk, dir;
+  };
+  std::vector<std::vector<Msg>> send_by_rank(a->cfg.nrank), recv_by_rank(a->cfg.nrank);
+
+  for (int ic = 0; ic < g.nchunk; ic++) {
+    for (int dz = 0; dz < 3; dz++) {
+      for (int dy = 0; dy < 3; dy++) {
+        for (int dx = 0; dx < 3; dx++) {
+          int k    = 9 * dz + 3 * dy + dx;
+          int nbid = a->nbid[(size_t)ic * NBSIZE + k];
+          int nbrk = a->nbrank[(size_t)ic * NBSIZE + k];
+          int code = NB_NONE;
+          if (nbid >= 0 && dir_active(g, dz, dy, dx)) {
+            if (nbrk == myrank) {
+              code = nbid - a->chunk_begin;
+            } else {
+              // provisional: remote, slot assigned below
+              code = NB_REMOTE_BASE;
+              int opp = 9 * (2 - dz) + 3 * (2 - dy) + (2 - dx);
+              send_by_rank[nbrk].push_back({a->chunk_begin + ic, k, ic, k});
+              recv_by_rank[nbrk].push_back({nbid, opp, ic, k});
+            }
+          }
+          a->nbr_code[(size_t)ic * NBSIZE + k] = code;
+        }
+      }
+    }
+  }
+
+  auto by_sender = [](const Msg& x, const Msg& y) {
+    return std::tie(x.sender_id, x.sender_dir) < std::tie(y.sender_id, y.sender_dir);
+  };
+
+  a->peers.clear();
+  a->slot_peer.clear();
+  for (int r = 0; r < a->cfg.nrank; r++) {
+    if (send_by_rank[r].empty() && recv_by_rank[r].empty())
+      continue;
+    std::sort(send_by_rank[r].begin(), send_by_rank[r].end(), by_sender);
+    std::sort(recv_by_rank[r].begin(), recv_by_rank[r].end(), by_sender);
+
+    PeerPlan p;
+    p.rank = r;
+    for (int mode = 0; mode < 2; mode++) {
+      int     ncomp = mode == 0 ? 6 : 4;
+      int64_t off   = 0;
+      for (auto& m : send_by_rank[r]) {
+        p.send_msg_off[mode].push_back(off);
+        off += region_elems(g, m.dir, ncomp);
+      }
+      p.send_elems[mode] = off;
+      off                = 0;
+      for (auto& m : recv_by_rank[r]) {
+        p.recv_msg_off[mode].push_back(off);
+        off += region_elems(g, m.dir, ncomp);
+      }
+      p.recv_elems[mode] = off;
+    }
+    int peer_index = (int)a->peers.size();
+    for (auto& m : send_by_rank[r]) {
+      p.send_chunk.push_back(m.chunk);
+      p.send_dir.push_back(m.dir);
+      // one remote slot per (chunk, dir); the slot only needs to identify the peer
+      int slot = (int)a->slot_peer.size();
+      a->slot_peer.push_back(peer_index);
+      a->nbr_code[(size_t)m.chunk * NBSIZE + m.dir] = NB_REMOTE_BASE - slot;
+    }
+    for (auto& m : recv_by_rank[r]) {
+      p.recv_chunk.push_back(m.chunk);
+      p.recv_dir.push_back(m.dir);
+    }
+    a->peers.push_back(std::move(p));
+  }
+
+  PICNIX_CUDA(a, cudaMemcpy(a->d.nbr, a->nbr_code.data(), a->nbr_code.size() * sizeof(int),
+                            cudaMemcpyHostToDevice));
+
+  // device side of the plan
+  int status;
+  for (auto& p : a->peers) {
+    std::vector<int> sdesc, rdesc;
+    for (size_t m = 0; m < p.send_chunk.size(); m++) {
+      sdesc.push_back(p.send_chunk[m]);
+      sdesc.push_back(p.send_dir[m]);
+    }
+    for (size_t m = 0; m < p.recv_chunk.size(); m++) {
+      rdesc.push_back(p.recv_chunk[m]);
+      rdesc.push_back(p.recv_dir[m]);
+    }
+    if ((status = upload_vector(a, &p.d_send_desc, sdesc)) != PICNIX_OK)
+      return status;
+    if ((status = upload_vector(a, &p.d_recv_desc, rdesc)) != PICNIX_OK)
+      return status;
+    for (int mode = 0; mode < 2; mode++) {
+      if ((status = upload_vector(a, &p.d_send_off[mode], p.send_msg_off[mode])) != PICNIX_OK)
+        return status;
+      if ((status = upload_vector(a, &p.d_recv_off[mode], p.recv_msg_off[mode])) != PICNIX_OK)
+        return status;
+      PICNIX_CUDA(a, cudaMalloc((void**)&p.d_send[mode],
+                                std::max<int64_t>(p.send_elems[mode], 1) * sizeof(double)));
+      PICNIX_CUDA(a, cudaMalloc((void**)&p.d_recv[mode],
+                                std::max<int64_t>(p.recv_elems[mode], 1) * sizeof(double)));
+    }
+    PICNIX_CUDA(a, cudaMalloc((void**)&p.d_psend_count, 2 * sizeof(int)));
+    PICNIX_CUDA(a, cudaMemset(p.d_psend_count, 0, 2 * sizeof(int)));
+  }
+  if (!a->slot_peer.empty()) {
+    if ((status = upload_vector(a, &a->d_slot_peer, a->slot_peer)) != PICNIX_OK)
+      return status;
+  }
+  // global neighbour ids on the device (destination tags of remote particle records)
+  {
+    std::vector<int> nbid(a->nbid.begin(), a->nbid.end());
+    if ((status = upload_vector(a, &a->d_slot_dst, nbid)) != PICNIX_OK)
+      return status;
+  }
+  return PICNIX_OK;
+}
+
+// Particle staging buffers depend on the particle capacity, so they are sized lazily:
+// a fraction of the largest local population per peer (records of 64 B).
+static int ensure_particle_staging(picnix_arena* a)
+{
+  if (a->peers.empty() || a->d_psend_ptrs != nullptr)
+    return PICNIX_OK;
+  int64_t total_cap = 0;
+  for (int s = 0; s < a->nseg; s++)
+    total_cap += a->seg_cap[s];
+  // everything that can leave through one face in a step is far below 1/4 of the population
+  int64_t cap = std::max<int64_t>(4096, total_cap / 4);
+  std::vector<double*> ptrs;
+  std::vector<int*>    cnts;
+  std::vector<int64_t> caps;
+  for (auto& p : a->peers) {
+    p.pcap_send = cap;
+    p.pcap_recv = cap;
+    PICNIX_CUDA(a, cudaMalloc((void**)&p.d_psend, cap * 8 * sizeof(double)));
+    PICNIX_CUDA(a, cudaMalloc((void**)&p.d_precv, cap * 8 * sizeof(double)));
+    ptrs.push_back(p.d_psend);
+    cnts.push_back(p.d_psend_count);
+    caps.push_back(cap);
+  }
+  int status;
+  if ((status = upload_vector(a, &a->d_psend_ptrs, ptrs)) != PICNIX_OK)
+    return status;
+  if ((status = upload_vector(a, &a->d_psend_cnts, cnts)) != PICNIX_OK)
+    return status;
+  if ((status = upload_vector(a, &a->d_psend_caps, caps)) != PICNIX_OK)
+    return status;
+  return PICNIX_OK;
+}
+
+int launch_halo_begin(picnix_arena* a, int mode)
+{
+  const Geom& g      = a->g;
+  int64_t     ncell  = (int64_t)g.nchunk * g.Ng;
+  int         blocks = (int)((ncell + HALO_THREADS - 1) / HALO_THREADS);
+
+  switch (mode) {
+  case PICNIX_BOUNDARY_EMF: {
+    // remote: pack interior margins first (they are not modified by the local gather)
+    for (auto& p : a->peers) {
+      int nmsg = (int)p.send_chunk.size();
+      if (nmsg > 0) {
+        remote_halo_kernel<6, false, true><<<nmsg, HALO_THREADS, 0, a->stream>>>(
+            g, a->d.uf, p.d_send_desc, p.d_send_off[0], p.d_send[0]);
+        a->kernel_launches++;
+      }
+    }
+    field_halo_local_kernel<<<blocks, HALO_THREADS, 0, a->stream>>>(g, a->d);
+    a->kernel_launches++;
+    break;
+  }
+  case PICNIX_BOUNDARY_CUR: {
+    // remote: pack ghost regions (read-only for the local gather as well)
+    for (auto& p : a->peers) {
+      int nmsg = (int)p.send_chunk.size();
+      if (nmsg > 0) {
+        remote_halo_kernel<4, true, true><<<nmsg, HALO_THREADS, 0, a->stream>>>(
+            g, a->d.uj, p.d_send_desc, p.d_send_off[1], p.d_send[1]);
+        a->kernel_launches++;
+      }
+    }
+    current_halo_local_kernel<<<blocks, HALO_THREADS, 0, a->stream>>>(g, a->d);
+    a->kernel_launches++;
+    break;
+  }
+  case PICNIX_BOUNDARY_PARTICLE: {
+    if (!a->particles_allocated)
+      return fail(a, PICNIX_ERR_INVALID, "no particles allocated");
+    int status = ensure_particle_staging(a);
+    if (status != PICNIX_OK)
+      return status;
+    for (auto& p : a->peers)
+      PICNIX_CUDA(a, cudaMemsetAsync(p.d_psend_count, 0, sizeof(int), a->stream));
+    int maxcap = 0;
+    for (int s = 0; s < a->nseg; s++)
+      maxcap = std::max(maxcap, a->seg_cap[s]);
+    int bps = (maxcap + HALO_THREADS - 1) / HALO_THREADS;
+    if (bps > 0) {
+      MigrateTables tab{a->d_slot_peer, a->d_psend_ptrs, a->d_psend_cnts, a->d_psend_caps,
+                        a->d_slot_dst};
+      migrate_kernel<<<bps * a->nseg, HALO_THREADS, 0, a->stream>>>(g, a->d, tab, bps);
+      a->kernel_launches++;
+    }
+    // exact send sizes must be known to the host before the transfer (like MPI_Get_count)
+    for (auto& p : a->peers) {
+      int count = 0;
+      PICNIX_CUDA(a, cudaMemcpyAsync(&count, p.d_psend_count, sizeof(int), cudaMemcpyDeviceToHost,
+                                     a->stream));
+      PICNIX_CUDA(a, cudaStreamSynchronize(a->stream));
+      count         = (int)std::min<int64_t>(count, p.pcap_send);
+      p.psend_bytes = (int64_t)count * 8 * sizeof(double);
+      p.precv_bytes = 0;
+    }
+    break;
+  }
+  default:
+    return fail(a, PICNIX_ERR_INVALID, "No such boundary mode exists!");
+  }
+  return check_cuda(a, cudaGetLastError(), "boundary_begin");
+}
+
+int launch_halo_end(picnix_arena* a, int mode)
+{
+  const Geom& g = a->g;
+  switch (mode) {
+  case PICNIX_BOUNDARY_EMF:
+    for (auto& p : a->peers) {
+      int nmsg = (int)p.recv_chunk.size();
+      if (nmsg > 0) {
+        remote_halo_kernel<6, false, false><<<nmsg, HALO_THREADS, 0, a->stream>>>(
+            g, a->d.uf, p.d_recv_desc, p.d_recv_off[0], p.d_recv[0]);
+        a->kernel_launches++;
+      }
+    }
+    break;
+  case PICNIX_BOUNDARY_CUR:
+    for (auto& p : a->peers) {
+      int nmsg = (int)p.recv_chunk.size();
+      if (nmsg > 0) {
+        remote_halo_kernel<4, true, false><<<nmsg, HALO_THREADS, 0, a->stream>>>(
+            g, a->d.uj, p.d_recv_desc, p.d_recv_off[1], p.d_recv[1]);
+        a->kernel_launches++;
+      }
+    }
+    break;
+  case PICNIX_BOUNDARY_PARTICLE: {
+    for (auto& p : a->peers) {
+      int nrec = (int)(p.precv_bytes / (8 * sizeof(double)));
+      if (nrec > 0) {
+        unpack_particle_kernel<<<(nrec + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, 0,
+                                 a->stream>>>(g, a->d, p.d_precv, nrec, a->chunk_begin);
+        a->kernel_launches++;
+      }
+    }
+    // post_unpack ends with sort() for every species (nix/xtensor_halo3d.hpp:495-497)
+    int status = launch_sort(a, 0, -1);
+    if (status != PICNIX_OK)
+      return status;
+    break;
+  }
+  default:
+    return fail(a, PICNIX_ERR_INVALID, "No such boundary mode exists!");
+  }
+  return check_cuda(a, cudaGetLastError(), "boundary_end");
+}
+
+} // namespace picnix
+
+using namespace picnix;
+
+extern "C" {
+
+int picnix_cuda_get_peers(const picnix_arena_t* a, int32_t* npeer, int32_t* peer_rank)
+{
+  if (a == nullptr || npeer == nullptr)
+    return PICNIX_ERR_INVALID;
+  *npeer = (int32_t)a->peers.size();
+  if (peer_rank != nullptr) {
+    for (size_t i = 0; i < a->peers.size(); i++)
+      peer_rank[i] = a->peers[i].rank;
+  }
+  return PICNIX_OK;
+}
+
+int picnix_cuda_get_comm_buffer(picnix_arena_t* a, int32_t mode, int32_t peer_index,
+                                void** send_ptr, int64_t* send_bytes, void** recv_ptr,
+                                int64_t* recv_bytes)
+{
+  if (a == nullptr || peer_index < 0 || peer_index >= (int)a->peers.size())
+    return PICNIX_ERR_INVALID;
+  PeerPlan& p = a->peers[peer_index];
+  if (mode == PICNIX_BOUNDARY_EMF || mode == PICNIX_BOUNDARY_CUR) {
+    *send_ptr   = p.d_send[mode];
+    *recv_ptr   = p.d_recv[mode];
+    *send_bytes = p.send_elems[mode] * (int64_t)sizeof(double);
+    *recv_bytes = p.recv_elems[mode] * (int64_t)sizeof(double);
+    return PICNIX_OK;
+  }
+  if (mode == PICNIX_BOUNDARY_PARTICLE) {
+    int status = ensure_particle_staging(a);
+    if (status != PICNIX_OK)
+      return status;
+    *send_ptr   = p.d_psend;
+    *recv_ptr   = p.d_precv;
+    *send_bytes = p.psend_bytes;
+    *recv_bytes = p.precv_bytes;
+    return PICNIX_OK;
+  }
+  return fail(a, PICNIX_ERR_INVALID, "No such boundary mode exists!");
+}
+
+int picnix_cuda_set_recv_bytes(picnix_arena_t* a, int32_t mode, int32_t peer_index,
+                               int64_t recv_bytes)
+{
+  if (a == nullptr || peer_index < 0 || peer_index >= (int)a->peers.size() ||
+      mode != PICNIX_BOUNDARY_PARTICLE)
+    return PICNIX_ERR_INVALID;
+  PeerPlan& p = a->peers[peer_index];
+  if (recv_bytes < 0 || recv_bytes > p.pcap_recv * 8 * (int64_t)sizeof(double))
+    return fail(a, PICNIX_ERR_OVERFLOW, "particle receive buffer too small");
+  p.precv_bytes = recv_bytes;
+  return PICNIX_OK;
+}
+
+} // extern "C"

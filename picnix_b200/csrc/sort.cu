@@ -1,0 +1,150 @@
+// -*- C++ -*-
+// K4: counting sort that keeps particles cell-ordered, batched over all (chunk, species) segments.
+//
+// Reference: XtensorParticle::sort (nix/xtensor_particle.hpp:260-321).  The reference stripes its
+// histogram over NIX_SIMD_WIDTH lanes and scatters in the order (cell, ip % 8, ip); only
+// `pindex`, `Np` and the SET of particles in each cell are implementation independent
+// (SURVEY Appendix A), and those are what this kernel reproduces bit-exactly:
+//   pindex[k] = number of particles with key < k   (k = 0..Ng),   Np = pindex[Ng]
+// Particles whose key is Ng (outside the chunk) are dropped.
+//
+// Three steps, all on the arena's stream, no host round trip:
+//   1. exclusive scan of the per-segment histogram pcount -> pindex, and pcount <- pindex (cursor)
+//   2. scatter xu -> xv with one atomic cursor bump per particle (order inside a cell is free)
+//   3. Np <- pindex[Ng], tail counter <- 0; the host swaps the xu/xv pointers
+#include "arena.hpp"
+
+namespace picnix
+{
+
+namespace
+{
+
+constexpr int SCAN_THREADS    = 256;
+constexpr int SCATTER_THREADS = 256;
+
+__device__ __forceinline__ int warp_inclusive_scan(int v)
+{
+#pragma unroll
+  for (int ofs = 1; ofs < 32; ofs <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, v, ofs);
+    if ((threadIdx.x & 31) >= ofs)
+      v += n;
+  }
+  return v;
+}
+
+// one block per segment; bins are consumed in tiles of SCAN_THREADS with a running carry
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(Geom g, DevPtrs d, int seg0)
+{
+  __shared__ int warp_sum[SCAN_THREADS / 32];
+  __shared__ int carry;
+
+  const int     seg  = seg0 + blockIdx.x;
+  const int     nbin = g.Ng + 1;
+  int*          cnt  = d.pcount + (int64_t)seg * nbin;
+  int*          pix  = d.pindex + (int64_t)seg * nbin;
+  const int     lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0)
+    carry = 0;
+  __syncthreads();
+
+  for (int base = 0; base < nbin; base += SCAN_THREADS) {
+    int k = base + threadIdx.x;
+    int c = k < nbin ? cnt[k] : 0;
+    int s = warp_inclusive_scan(c);
+    if (lane == 31)
+      warp_sum[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      int w = lane < SCAN_THREADS / 32 ? warp_sum[lane] : 0;
+      w     = warp_inclusive_scan(w);
+      if (lane < SCAN_THREADS / 32)
+        warp_sum[lane] = w;
+    }
+    __syncthreads();
+    int prefix = carry + (warp > 0 ? warp_sum[warp - 1] : 0) + s - c; // exclusive
+    if (k < nbin) {
+      pix[k] = prefix;
+      cnt[k] = prefix; // scatter cursor
+    }
+    __syncthreads();
+    if (threadIdx.x == SCAN_THREADS - 1)
+      carry = prefix + c;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(SCATTER_THREADS)
+scatter_kernel(Geom g, DevPtrs d, int seg0, int blocks_per_seg)
+{
+  const int lseg = blockIdx.x / blocks_per_seg;
+  const int b    = blockIdx.x - lseg * blocks_per_seg;
+  const int seg  = seg0 + lseg;
+  const int ip   = b * blockDim.x + threadIdx.x;
+  // own particles plus the migrants appended behind them during this step
+  const int n    = min(d.np[seg] + d.ntail[seg], d.seg_cap[seg]);
+  if (ip >= n)
+    return;
+
+  const int64_t off = d.seg_off[seg];
+  const int     key = d.gindex[off + ip];
+  if (key >= g.Ng)
+    return; // left the chunk: discarded (nix/xtensor_particle.hpp:319-320)
+
+  const int dst = atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, 1);
+#pragma unroll
+  for (int k = 0; k < NC; k++)
+    d.xv[k * d.pcap + off + dst] = d.xu[k * d.pcap + off + ip];
+}
+
+__global__ void finish_kernel(Geom g, DevPtrs d, int seg0, int nseg)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nseg)
+    return;
+  int seg      = seg0 + t;
+  d.np[seg]    = d.pindex[(int64_t)seg * (g.Ng + 1) + g.Ng];
+  d.ntail[seg] = 0;
+}
+
+} // namespace
+
+// XtensorParticle::sort for segments of chunks [c0, c0+cn); the histogram must be current
+int launch_sort(picnix_arena* a, int c0, int cn)
+{
+  resolve_range(a, c0, cn);
+  if (!a->particles_allocated)
+    return fail(a, PICNIX_ERR_INVALID, "no particles allocated");
+  if (cn == 0)
+    return PICNIX_OK;
+  if (c0 != 0 || cn != a->g.nchunk)
+    return fail(a, PICNIX_ERR_INVALID,
+                "sort_particle acts on all chunks of the arena (xu/xv are swapped arena-wide)");
+
+  const Geom& g    = a->g;
+  const int   seg0 = c0 * g.Ns;
+  const int   nseg = cn * g.Ns;
+
+  scan_kernel<<<nseg, SCAN_THREADS, 0, a->stream>>>(g, a->d, seg0);
+  a->kernel_launches++;
+
+  int maxcap = 0;
+  for (int s = seg0; s < seg0 + nseg; s++)
+    maxcap = std::max(maxcap, a->seg_cap[s]);
+  int bps = (maxcap + SCATTER_THREADS - 1) / SCATTER_THREADS;
+  if (bps > 0) {
+    scatter_kernel<<<bps * nseg, SCATTER_THREADS, 0, a->stream>>>(g, a->d, seg0, bps);
+    a->kernel_launches++;
+  }
+  finish_kernel<<<(nseg + 127) / 128, 128, 0, a->stream>>>(g, a->d, seg0, nseg);
+  a->kernel_launches++;
+  PICNIX_CUDA(a, cudaGetLastError());
+
+  // XtensorParticle::swap (nix/xtensor_particle.hpp:120-123)
+  std::swap(a->d.xu, a->d.xv);
+  return PICNIX_OK;
+}
+
+} // namespace picnix
