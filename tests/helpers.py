@@ -86,3 +86,18 @@ def cells_consistent(sim):
             if pindex[-1] != n:
                 return False
     return True
+
+
+def keys_equal(a, b):
+    """Cell keys (gindex) bit-exact, matched by particle id (order inside a cell is free)."""
+    for ic in range(a.nchunk):
+        for isp in range(a.Ns):
+            pa, pb = a.get_particles(ic, isp), b.get_particles(ic, isp)
+            ka, kb = a.get_gindex(ic, isp), b.get_gindex(ic, isp)
+            if pa.shape != pb.shape:
+                return False
+            oa = np.argsort(pa[:, 6].view(np.int64), kind="stable")
+            ob = np.argsort(pb[:, 6].view(np.int64), kind="stable")
+            if not np.array_equal(ka[oa], kb[ob]):
+                return False
+    return True

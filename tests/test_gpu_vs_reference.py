@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 
 from helpers import (FIELD_FF, FIELD_UF, FIELD_UJ, MODE_CUR, MODE_EMF, MODE_PARTICLE, counts_equal, field_err,
-                     particle_err)
+                     keys_equal, particle_err)
 from oracle import ref_backend
 from picnix_b200 import problems
 
@@ -81,9 +81,7 @@ def test_velocity_position_orders(case, order):
     dx, du, same = particle_err(gpu, ref, scale_x=16.0, scale_u=10.0, which=1)
     assert same and dx < 1e-14 and du < 1e-13
     # keys computed by the position push
-    for ic in range(ref.nchunk):
-        for isp in range(ref.Ns):
-            assert np.array_equal(gpu.get_gindex(ic, isp), ref.get_gindex(ic, isp))
+    assert keys_equal(gpu, ref)
 
 
 @pytest.mark.parametrize("pusher", [0, 1, 2])
@@ -122,9 +120,7 @@ def test_fused_equals_separate(case):
     dx, du, same = particle_err(gpu, ref, scale_x=16.0, scale_u=10.0)
     assert same and dx < 1e-14 and du < 1e-13
     assert field_err(gpu, ref, FIELD_UJ) < 1e-12
-    for ic in range(ref.nchunk):
-        for isp in range(ref.Ns):
-            assert np.array_equal(gpu.get_gindex(ic, isp), ref.get_gindex(ic, isp))
+    assert keys_equal(gpu, ref)
 
 
 @pytest.mark.parametrize("case", ["t3d", "t2d", "ts1d"])
