@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- particle-pushes/s of the PIC-NIX per-timestep hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1], SURVEY.md §8d "T3D"): 3-D uniform thermal plasma, per GPU
+128x128x128 cells in 16^3-cell chunks (512 chunks), 2 species x 32 particles per cell = 64 ppc
+(1.34e8 particles), 2nd-order shape, Boris pusher, MC interpolation, cc=10, delt=0.05, delh=1, Bx=5,
+periodic.  One "step" is one full time step of PicApplication::push_openmp
+(pic/pic_application.cpp:219-292): B half step, interpolation + velocity + position push + cell key
++ Esirkepov deposit (one fused kernel), current halo, particle migration, B half step, E step,
+field halo, counting sort.  Weak scaling: every GPU owns its own 128^3 block of a larger periodic box.
+
+`value`    : particle-steps/s with all state resident in HBM, timed with CUDA events on the stream
+             the kernels run on, barrier + synchronize on both sides, max over ranks.
+`e2e`      : the same metric through picnix_cuda_step_host (HOST arrays in the reference's layouts
+             in, HOST arrays out, every step), i.e. what a host-resident PicChunk would see.
+`roofline` : the fused push+deposit kernel against the measured HBM copy bandwidth
+             (MEASURED_PEAKS.json), algorithmic bytes = 116 B/particle (R 56 + W 56 + 4 B key) plus
+             the field tile traffic per cell.
+`cpu_baseline` / `--impl reference` : the UNMODIFIED reference (oracle/_ref, its own OpenMP loop
+             over chunks and xsimd kernels) on all host cores, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-pushes/sec/GPU (push+deposit+sort), 3D thermal plasma 64 ppc order 2"
+UNIT = "particle-steps/s"
+
+# workload constants
+CC, DELT, DELH, BX = 10.0, 0.05, 1.0, 5.0
+ORDER, PUSHER, INTERP = 2, 0, 0
+CHUNK = 16
+PPC = (32, 32)
+
+# algorithmic bytes (DESIGN.md "Kernels and rooflines")
+BYTES_PUSH_PER_PARTICLE = 56 + 56 + 4          # fused push+deposit: read xu, write xu, write key
+BYTES_PUSH_PER_CELL = 48 + 2 * 32              # field tile read + J accumulate (RMW) per cell
+BYTES_STEP_PER_PARTICLE = 232                  # push pass + sort pass
+BYTES_STEP_PER_CELL = 600
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=128, help="cells per GPU per dimension")
+    ap.add_argument("--ppc", type=int, default=32, help="particles per cell per species")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-cells", type=int, default=64, help="cells per dimension of the CPU sample")
+    ap.add_argument("--ref-steps", type=int, default=0, help="override steps of the reference arm")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fp:
+            return json.load(fp)["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._reader, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _reader(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons, power = [], [], set(), []
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smmax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"],
+                                 f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smmax)), "reasons": sorted(reasons),
+                "power_w_max": float(max(power)), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference on the host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference(cells, ppc, steps, warmup):
+    from oracle import ref_backend
+    from picnix_b200 import problems
+
+    ndims = (cells, cells, cells)
+    cdims = tuple(n // CHUNK for n in ndims)
+    sim = ref_backend.RefSim(ndims, cdims, Ns=2, cc=CC, delh=DELH, order=ORDER, pusher=PUSHER, interp=INTERP,
+                             vector_mode=1, nthread=0)
+    problems.setup_uniform_plasma(sim, ndims, cdims, problems.THERMAL_SPECIES, (ppc, ppc), delh=DELH,
+                                  B0=(BX, 0.0, 0.0), seed=1)
+    npart = problems.total_particles(sim)
+    sim.step(DELT, warmup)
+    t0 = time.perf_counter()
+    sim.step(DELT, steps)
+    elapsed = time.perf_counter() - t0
+    lib = os.path.basename(ref_backend.library_path())
+    return {
+        "value": npart * steps / elapsed,
+        "ms_per_step": 1e3 * elapsed / steps,
+        "cores": sim.nthread,
+        "sample": f"{cells}^3 cells in {CHUNK}^3 chunks ({sim.nchunk} chunks), {2 * ppc} ppc, {npart} particles, "
+                  f"{steps} steps after {warmup} warm-up; reference 'vector' kernels + OpenMP over chunks, {lib}",
+        "particles": npart,
+    }
+
+
+def reference_main(args, rank, world):
+    if rank != 0:
+        return
+    steps = args.ref_steps if args.ref_steps > 0 else max(3, min(args.steps, 10))
+    warmup = max(1, min(args.warmup, 2))
+    res = run_reference(args.ref_cells, args.ppc, steps, warmup)
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
+                         "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, ngpu):
+    return {
+        "workload": f"thermal-3D (example/thermal with Nz,Ny>1): {args.cells}^3 cells per GPU in {CHUNK}^3 chunks, "
+                    f"2 species x {args.ppc} ppc, order {ORDER}, Boris, MC, cc={CC}, delt={DELT}, Bx={BX}, periodic",
+        "cells_per_gpu": args.cells ** 3, "chunks_per_gpu": (args.cells // CHUNK) ** 3,
+        "particles_per_gpu": args.cells ** 3 * 2 * args.ppc, "parallelism": f"chunk decomposition over {ngpu} GPU(s)",
+        "l2_policy": "inputs (15 GB of particles per GPU) are far larger than the 126 MB L2; no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def gpu_layout(ngpu):
+    """Arrangement of the per-GPU blocks: 1,2,4,8 GPUs -> (1,1,1),(1,1,2),(1,2,2),(2,2,2)."""
+    return {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}[ngpu]
+
+
+def b200_main(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from picnix_b200 import capi, problems
+    from picnix_b200.distributed import DistributedSim
+
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    lay = gpu_layout(world)
+    ndims = tuple(args.cells * l for l in lay)
+    cdims = tuple(n // CHUNK for n in ndims)
+    sim = DistributedSim(ndims, cdims, Ns=2, cc=CC, delh=DELH, order=ORDER, pusher=PUSHER, interp=INTERP,
+                         rank=rank, world=world, block_layout=lay)
+    stream = torch.cuda.Stream()
+    sim.set_stream(stream.cuda_stream)
+    problems.setup_uniform_plasma(sim, ndims, cdims, problems.THERMAL_SPECIES, (args.ppc, args.ppc), delh=DELH,
+                                  B0=(BX, 0.0, 0.0), seed=1, chunk_id_begin=sim.chunk_id_begin)
+    np_local = int(sim.get_np_all().sum())
+    ncell_local = args.cells ** 3
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            sim.step_phases(DELT)
+        barrier()
+        launches0, _ = sim.counters()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(args.steps)]
+        ev0.record(stream)
+        for k in range(args.steps):
+            sim.step_phases(DELT, kernel_events=kev[k])
+        ev1.record(stream)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        launches1, _ = sim.counters()
+
+    elapsed_ms = ev0.elapsed_time(ev1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    sim.synchronize()  # raises on device-side overflow flags
+    np_after = int(sim.get_np_all().sum())
+
+    t = torch.tensor([elapsed_ms, float(np_local), float(np_after), kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms = float(tmax[0])
+        kernel_ms = float(tmax[3])
+        np_total = float(tsum[1])
+        np_after_total = float(tsum[2])
+    else:
+        np_total, np_after_total = float(np_local), float(np_after)
+
+    value = np_total * args.steps / (elapsed_ms * 1e-3)
+
+    # roofline of the dominant kernel (fused push + deposit), per launch on this rank
+    peak, peak_src = measured_peaks()
+    alg_bytes = np_local * BYTES_PUSH_PER_PARTICLE + ncell_local * BYTES_PUSH_PER_CELL
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    step_bytes = np_local * BYTES_STEP_PER_PARTICLE + ncell_local * BYTES_STEP_PER_CELL
+    roofline = {
+        "bound": "hbm", "kernel": "push_deposit_fused", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * args.steps / elapsed_ms,
+        "algorithmic_bytes_per_launch": alg_bytes,
+        "whole_step": {"achieved": step_bytes * args.steps / (elapsed_ms * 1e-3) / 1e9 * (1 if world == 1 else 1),
+                       "frac": step_bytes * args.steps / (elapsed_ms * 1e-3) / 1e9 / peak,
+                       "bytes_per_step": step_bytes},
+    }
+
+    # e2e: host arrays in, host arrays out, every step (rank-local arenas; N=1 only has no peers)
+    e2e = None
+    if not args.no_e2e and world == 1:
+        e2e = sim.measure_e2e(DELT, args.e2e_steps)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        try:
+            res = run_reference(args.ref_cells, args.ppc, 5, 1)
+            cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
+                   "sample": res["sample"]}
+        except Exception as exc:  # the reference binary is absent: say so instead of inventing a number
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {exc}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world),
+            "per_gpu": value / world,
+            "particles_before_after": [np_total, np_after_total],
+            "clocks": clocks,
+            "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0,
+                                                "d2h_bytes_per_step": 0, "note": "measured at N=1 only"},
+            "gpu_launches": int(launches1 - launches0),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        reference_main(args, rank, world)
+    else:
+        b200_main(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -106,6 +106,10 @@ int picnix_cuda_arena_create(const picnix_config_t* cfg, const int32_t* boundary
 int picnix_cuda_arena_destroy(picnix_arena_t* arena);
 const char* picnix_cuda_last_error(const picnix_arena_t* arena);
 
+/* tuning / testing switches: "force_generic" = 1 bypasses the tiled 3-D kernels (row-owner
+ * deposit) so the thread-per-particle kernels run instead */
+int picnix_cuda_set_option(picnix_arena_t* arena, const char* key, int64_t value);
+
 /* use an existing CUDA stream (cudaStream_t as void*); default is a stream the arena owns */
 int picnix_cuda_set_stream(picnix_arena_t* arena, void* stream);
 int picnix_cuda_synchronize(picnix_arena_t* arena);

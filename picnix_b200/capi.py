@@ -59,6 +59,7 @@ SIGNATURES = {
     "picnix_cuda_arena_create": (_i32, [C.POINTER(Config), C.c_void_p, C.POINTER(_vp)]),
     "picnix_cuda_arena_destroy": (_i32, [_vp]),
     "picnix_cuda_last_error": (C.c_char_p, [_vp]),
+    "picnix_cuda_set_option": (_i32, [_vp, C.c_char_p, _i64]),
     "picnix_cuda_set_stream": (_i32, [_vp, _vp]),
     "picnix_cuda_synchronize": (_i32, [_vp]),
     "picnix_cuda_get_layout": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), _pi, C.POINTER(_i32),

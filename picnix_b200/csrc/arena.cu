@@ -100,6 +100,7 @@ int upload_particles(picnix_arena* a, int ichunk, int is, const double* aos, int
   if (np < 0 || np > a->seg_cap[seg])
     return fail(a, PICNIX_ERR_OVERFLOW, "upload_particles: np exceeds segment capacity");
 
+  a->pindex_valid = false; // the new particles are not cell-ordered until the next sort
   int64_t elems = (int64_t)np * NC;
   if (np > 0) {
     int status = ensure_stage(a, elems);

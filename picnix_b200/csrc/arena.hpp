@@ -127,6 +127,8 @@ struct picnix_arena {
   double*                d_stage     = nullptr;
   int64_t                stage_elems = 0;
   bool                   particles_allocated = false;
+  bool                   pindex_valid = false;  // pindex matches the particle order (after a sort)
+  bool                   force_generic = false; // testing: bypass the tiled kernels
   int64_t                kernel_launches = 0;
   int64_t                particle_pushes = 0;
   int64_t                np_total_hint   = 0; // sum of np at last host-visible count
@@ -171,6 +173,8 @@ int launch_push_velocity(picnix_arena* a, int c0, int cn, double delt);
 int launch_push_position(picnix_arena* a, int c0, int cn, double delt);
 int launch_deposit_current(picnix_arena* a, int c0, int cn, double delt);
 int launch_push_deposit_fused(picnix_arena* a, int c0, int cn, double delt);
+int launch_deposit_rows(picnix_arena* a, int c0, int cn, double delt);
+bool row_kernel_applies(const picnix_arena* a);
 
 int launch_count(picnix_arena* a, int c0, int cn);
 int launch_sort(picnix_arena* a, int c0, int cn);

@@ -23,6 +23,17 @@ inline bool bad_range(const picnix_arena* a, int c0, int cn)
 
 extern "C" {
 
+int picnix_cuda_set_option(picnix_arena_t* a, const char* key, int64_t value)
+{
+  if (a == nullptr || key == nullptr)
+    return PICNIX_ERR_INVALID;
+  if (std::string(key) == "force_generic") {
+    a->force_generic = value != 0;
+    return PICNIX_OK;
+  }
+  return fail(a, PICNIX_ERR_INVALID, std::string("unknown option: ") + key);
+}
+
 int picnix_cuda_init_friedman(picnix_arena_t* a, int32_t c0, int32_t cn)
 {
   PICNIX_CHECK_RANGE(a, c0, cn);

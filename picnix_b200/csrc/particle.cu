@@ -292,6 +292,8 @@ int launch_deposit_current(picnix_arena* a, int c0, int cn, double delt)
   // fill_all(uj, 0), pic/engine/current.hpp:91,152
   PICNIX_CUDA(a, cudaMemsetAsync(a->d.uj + (int64_t)c0 * a->g.Ng * 4, 0,
                                  (size_t)cn * a->g.Ng * 4 * sizeof(double), a->stream));
+  if (row_kernel_applies(a))
+    return launch_deposit_rows(a, c0, cn, delt);
   int bps = blocks_per_segment(a, c0, cn);
   if (bps == 0)
     return PICNIX_OK;

@@ -144,6 +144,7 @@ int launch_sort(picnix_arena* a, int c0, int cn)
 
   // XtensorParticle::swap (nix/xtensor_particle.hpp:120-123)
   std::swap(a->d.xu, a->d.xv);
+  a->pindex_valid = true;
   return PICNIX_OK;
 }
 

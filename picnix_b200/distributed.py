@@ -1,0 +1,181 @@
+"""One-process-per-GPU driver: the reference's MPI rank decomposition mapped onto torch.distributed.
+
+The reference gives every MPI rank a contiguous range of space-filling-curve chunk ids
+(nix/application.cpp:245-309, nix/balancer.cpp:101-124) and exchanges three halos per step between
+neighbouring chunks (pic/pic_application.cpp:219-292).  Here every rank owns one device arena; halos
+between chunks of the same arena never leave the GPU, and the chunks owned by another rank are
+served by ONE aggregated send and ONE receive buffer per peer and mode, moved with NCCL send/recv
+(batched in a single group) over NVLink.  torch.distributed is plumbing only: rendezvous, the
+send/recv of the buffers the CUDA library packed, and the final timing reduction.
+
+`Transport` is backend agnostic (device buffers for the CUDA arena, host buffers for the CPU oracle
+that the gloo tests use), so the message planning is covered by world_size-2 CPU tests.
+"""
+import time
+
+import numpy as np
+
+from . import capi
+from .simulation import CudaSim
+
+MODE_EMF, MODE_CUR, MODE_MOM, MODE_PARTICLE = 0, 1, 2, 3
+
+
+class _CudaBuffer:
+    """Zero-copy view of a raw device pointer for torch.as_tensor."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def cuda_view(ptr, nbytes):
+    import torch
+
+    if nbytes == 0:
+        return torch.empty(0, dtype=torch.uint8, device="cuda")
+    return torch.as_tensor(_CudaBuffer(ptr, nbytes), device="cuda")
+
+
+def host_view(ptr, nbytes):
+    import ctypes
+
+    import torch
+
+    if nbytes == 0:
+        return torch.empty(0, dtype=torch.uint8)
+    arr = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(nbytes,))
+    return torch.from_numpy(arr)
+
+
+class Transport:
+    """Moves the per-peer halo buffers of `sim` between ranks with torch.distributed."""
+
+    def __init__(self, sim, world, device_buffers=True):
+        self.sim = sim
+        self.world = world
+        self.view = cuda_view if device_buffers else host_view
+        self.device = "cuda" if device_buffers else "cpu"
+        self.peers = sim.peers() if world > 1 else []
+
+    def _exchange(self, pairs):
+        import torch.distributed as dist
+
+        ops = []
+        for peer, send, recv in pairs:
+            if recv.numel() > 0:
+                ops.append(dist.P2POp(dist.irecv, recv, peer))
+            if send.numel() > 0:
+                ops.append(dist.P2POp(dist.isend, send, peer))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def move(self, mode):
+        """Between boundary_begin(mode) and boundary_end(mode): send -> peer's recv buffer."""
+        if not self.peers:
+            return
+        import torch
+
+        if mode == MODE_PARTICLE:
+            # variable size: first the byte counts (the reference sizes its receive with
+            # MPI_Iprobe + MPI_Get_count, nix/chunk.cpp:329-345), then the payload
+            bufs = [self.sim.comm_buffer(mode, i) for i in range(len(self.peers))]
+            scount = [torch.tensor([b[1]], dtype=torch.int64, device=self.device) for b in bufs]
+            rcount = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in bufs]
+            self._exchange([(p, s, r) for p, s, r in zip(self.peers, scount, rcount)])
+            for i, r in enumerate(rcount):
+                self.sim.set_recv_bytes(mode, i, int(r.item()))
+        pairs = []
+        for i, peer in enumerate(self.peers):
+            sp, sb, rp, rb = self.sim.comm_buffer(mode, i)
+            pairs.append((peer, self.view(sp, sb), self.view(rp, rb)))
+        self._exchange(pairs)
+
+
+class DistributedSim(CudaSim):
+    """CudaSim whose chunk ids are split over `world` ranks like the reference's MPI ranks."""
+
+    def __init__(self, ndims, cdims, Ns, cc, rank=0, world=1, block_layout=None, boundary=None, **kw):
+        super().__init__(ndims, cdims, Ns, cc, nrank=world, rank=rank, boundary=boundary, **kw)
+        self.rank, self.world = rank, world
+        self.transport = Transport(self, world, device_buffers=True)
+
+    def exchange(self, mode):
+        self.boundary_begin(mode)
+        self.transport.move(mode)
+        self.boundary_end(mode)
+
+    def step_phases(self, dt, kernel_events=None):
+        """One time step, PicApplication::push_openmp order, transports between begin and end."""
+        self.commit()
+        lib, h, chk = self.lib, self.h, self._check
+        chk(lib.picnix_cuda_push_bfd(h, 0, -1, 0.5 * dt))
+        if kernel_events is not None:
+            kernel_events[0].record()
+        chk(lib.picnix_cuda_push_deposit_fused(h, 0, -1, dt))
+        if kernel_events is not None:
+            kernel_events[1].record()
+        chk(lib.picnix_cuda_boundary_begin(h, MODE_CUR))
+        self.transport.move(MODE_CUR)
+        chk(lib.picnix_cuda_boundary_begin(h, MODE_PARTICLE))
+        self.transport.move(MODE_PARTICLE)
+        chk(lib.picnix_cuda_push_bfd(h, 0, -1, 0.5 * dt))
+        chk(lib.picnix_cuda_boundary_end(h, MODE_CUR))
+        chk(lib.picnix_cuda_push_efd(h, 0, -1, dt))
+        chk(lib.picnix_cuda_boundary_begin(h, MODE_EMF))
+        self.transport.move(MODE_EMF)
+        chk(lib.picnix_cuda_boundary_end(h, MODE_PARTICLE))
+        chk(lib.picnix_cuda_boundary_end(h, MODE_EMF))
+
+    def step(self, dt, nstep=1):
+        if self.world == 1:
+            return super().step(dt, nstep)
+        for _ in range(nstep):
+            self.step_phases(dt)
+
+    # -- end-to-end measurement through the host-buffer entry point -----------------------------
+    def measure_e2e(self, dt, nstep):
+        """particle-steps/s through picnix_cuda_step_host: host arrays in and out every step."""
+        import torch
+
+        assert self.world == 1
+        Ns, nchunk, ncell = self.Ns, self.nchunk, self.Ng
+        np_now = self.get_np_all().reshape(-1).astype(np.int32)
+        caps = np.array([int(n * (1 + self.cfg.buffer_ratio)) for n in np_now], dtype=np.int32)
+        caps = ((caps + 128) // 128) * 128
+
+        def pinned(n):
+            return torch.empty(int(n), dtype=torch.float64, pin_memory=True).numpy()
+
+        uf, uj, ff = pinned(nchunk * ncell * 6), pinned(nchunk * ncell * 4), pinned(nchunk * ncell * 18)
+        xu = pinned(int(caps.sum()) * 7)
+        # current device state -> host arrays (outside the timed region)
+        off = 0
+        for ic in range(nchunk):
+            uf[ic * ncell * 6:(ic + 1) * ncell * 6] = self.get_field(ic, capi.FIELD_UF).reshape(-1)
+            uj[ic * ncell * 4:(ic + 1) * ncell * 4] = self.get_field(ic, capi.FIELD_UJ).reshape(-1)
+            ff[ic * ncell * 18:(ic + 1) * ncell * 18] = self.get_field(ic, capi.FIELD_FF).reshape(-1)
+            for isp in range(Ns):
+                seg = ic * Ns + isp
+                n = int(np_now[seg])
+                xu[off * 7:(off + n) * 7] = self.get_particles(ic, isp, 0, n).reshape(-1)
+                off += int(caps[seg])
+        np_in = np_now.copy()
+        np_out = np.zeros_like(np_in)
+        h2d = d2h = 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(nstep):
+            self._check(self.lib.picnix_cuda_step_host(self.h, dt, 1, uf, uj, ff, xu, np_in, caps, np_out))
+            h2d += (uf.nbytes + uj.nbytes + ff.nbytes) + int(np_in.sum()) * 56
+            d2h += (uf.nbytes + uj.nbytes + ff.nbytes) + int(np_out.sum()) * 56
+            np_in, np_out = np_out.copy(), np_in
+        torch.cuda.synchronize()
+        elapsed = time.perf_counter() - t0
+        return {
+            "value": float(np_now.sum()) * nstep / elapsed, "unit": "particle-steps/s",
+            "h2d_bytes_per_step": h2d // nstep, "d2h_bytes_per_step": d2h // nstep, "steps": nstep,
+            "ms_per_step": 1e3 * elapsed / nstep,
+            "api": "picnix_cuda_step_host: reference-layout host arrays (uf, uj, ff, AoS particles) in and out "
+                   "every step",
+        }

@@ -77,6 +77,9 @@ class CudaSim:
     def synchronize(self):
         self._check(self.lib.picnix_cuda_synchronize(self.h))
 
+    def set_option(self, key, value):
+        self._check(self.lib.picnix_cuda_set_option(self.h, key.encode(), int(value)))
+
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.picnix_cuda_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
