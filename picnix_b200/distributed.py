@@ -92,6 +92,40 @@ class Transport:
         self._exchange(pairs)
 
 
+def step_phases(sim, transport, dt, kernel_events=None):
+    """One time step in the order of PicApplication::push_openmp (pic/pic_application.cpp:219-292).
+
+    `sim` is any backend with the chunk-level API (the CUDA arena, or the CPU oracle in the gloo
+    tests); `transport.move(mode)` carries the per-peer buffers between boundary_begin and
+    boundary_end.  Phase A: B half step, push + deposit, start the J and particle exchanges, B half
+    step; phase B: finish J, E step, start the E/B exchange; phases C-E: particles arrive (wrap,
+    count, sort), fields arrive.
+    """
+    sim.push_bfd(0.5 * dt)
+    if kernel_events is not None:
+        kernel_events[0].record()
+    sim.push_deposit_fused(dt)
+    if kernel_events is not None:
+        kernel_events[1].record()
+    sim.boundary_begin(MODE_CUR)
+    transport.move(MODE_CUR)
+    sim.boundary_begin(MODE_PARTICLE)
+    transport.move(MODE_PARTICLE)
+    sim.push_bfd(0.5 * dt)
+    sim.boundary_end(MODE_CUR)
+    sim.push_efd(dt)
+    sim.boundary_begin(MODE_EMF)
+    transport.move(MODE_EMF)
+    sim.boundary_end(MODE_PARTICLE)
+    sim.boundary_end(MODE_EMF)
+
+
+def exchange(sim, transport, mode):
+    sim.boundary_begin(mode)
+    transport.move(mode)
+    sim.boundary_end(mode)
+
+
 class DistributedSim(CudaSim):
     """CudaSim whose chunk ids are split over `world` ranks like the reference's MPI ranks."""
 
@@ -108,24 +142,7 @@ class DistributedSim(CudaSim):
     def step_phases(self, dt, kernel_events=None):
         """One time step, PicApplication::push_openmp order, transports between begin and end."""
         self.commit()
-        lib, h, chk = self.lib, self.h, self._check
-        chk(lib.picnix_cuda_push_bfd(h, 0, -1, 0.5 * dt))
-        if kernel_events is not None:
-            kernel_events[0].record()
-        chk(lib.picnix_cuda_push_deposit_fused(h, 0, -1, dt))
-        if kernel_events is not None:
-            kernel_events[1].record()
-        chk(lib.picnix_cuda_boundary_begin(h, MODE_CUR))
-        self.transport.move(MODE_CUR)
-        chk(lib.picnix_cuda_boundary_begin(h, MODE_PARTICLE))
-        self.transport.move(MODE_PARTICLE)
-        chk(lib.picnix_cuda_push_bfd(h, 0, -1, 0.5 * dt))
-        chk(lib.picnix_cuda_boundary_end(h, MODE_CUR))
-        chk(lib.picnix_cuda_push_efd(h, 0, -1, dt))
-        chk(lib.picnix_cuda_boundary_begin(h, MODE_EMF))
-        self.transport.move(MODE_EMF)
-        chk(lib.picnix_cuda_boundary_end(h, MODE_PARTICLE))
-        chk(lib.picnix_cuda_boundary_end(h, MODE_EMF))
+        step_phases(self, self.transport, dt, kernel_events)
 
     def step(self, dt, nstep=1):
         if self.world == 1:
