@@ -445,6 +445,11 @@ int picnix_cuda_arena_create(const picnix_config_t* cfg, const int32_t* boundary
     return status;
   if ((status = dev_alloc(a, &a->d_reduce, (size_t)g.nchunk * 4)) != PICNIX_OK)
     return status;
+  a->d.far_cap = 1 << 18;
+  if ((status = dev_alloc(a, &a->d.far_count, 1)) != PICNIX_OK)
+    return status;
+  if ((status = dev_alloc(a, &a->d.far_rec, (size_t)a->d.far_cap * 8, false)) != PICNIX_OK)
+    return status;
   if ((status = dev_alloc(a, &a->d.np, a->nseg)) != PICNIX_OK)
     return status;
   if ((status = dev_alloc(a, &a->d.ntail, a->nseg)) != PICNIX_OK)
@@ -488,6 +493,8 @@ int picnix_cuda_arena_destroy(picnix_arena_t* a)
   dev_free(a->d.pcount);
   dev_free(a->d.qm);
   dev_free(a->d.errflag);
+  dev_free(a->d.far_count);
+  dev_free(a->d.far_rec);
   dev_free(a->d_reduce);
   dev_free(a->d_stage);
   dev_free(a->d_slot_peer);
@@ -547,6 +554,8 @@ int picnix_cuda_synchronize(picnix_arena_t* a)
     return fail(a, PICNIX_ERR_OVERFLOW, "particle segment overflow (increase buffer_ratio)");
   if (flags[1] != 0)
     return fail(a, PICNIX_ERR_OVERFLOW, "particle migration send buffer overflow");
+  if (flags[3] != 0)
+    return fail(a, PICNIX_ERR_OVERFLOW, "too many particles moved more than one cell in a step");
   return PICNIX_OK;
 }
 

@@ -68,7 +68,11 @@ struct DevPtrs {
   int*     pindex;   // [nseg][Ng+1]
   int*     pcount;   // [nseg][Ng+1] histogram / scatter cursor
   double*  qm;       // [Ns][2] charge, mass
-  int*     errflag;  // [4] device-side error flags (0: segment overflow, 1: send overflow)
+  int*     errflag;  // [4] device-side error flags (0: segment overflow, 1: send overflow,
+                     //     2: bad migration tag, 3: far-mover list overflow)
+  int*     far_count; // [1] particles that moved more than one cell in the row kernel
+  double*  far_rec;   // [far_cap][8] x0,y0,z0,x1,y1,z1,q,chunk: deposited by a follow-up kernel
+  int      far_cap;
 };
 
 struct PeerPlan {

@@ -1,26 +1,30 @@
 // -*- C++ -*-
-// Row-owner Esirkepov deposit for 3-D, 2nd-order shapes (the BASELINE "T3D" configuration).
+// Row-owner push + Esirkepov deposit for 3-D, 2nd-order shapes (the BASELINE "T3D" configuration).
 //
 // Why: one fp64 atomic per stencil value (up to 5^3 x 4 per particle) is two orders of magnitude
-// too slow -- shared-memory fp64 atomics are CAS loops on sm_100a and L2 reductions saturate near
-// 1e11/s.  So nothing in the inner loop is atomic.  Instead
+// too slow -- shared-memory fp64 atomics are CAS loops on sm_100a and every L2 reduction costs an
+// LSU slot.  So nothing in the inner loop is atomic.  Instead
 //
-//   * a warp owns a ROW segment of RX cells (fixed z, y) and walks its cell-sorted particles;
-//   * phase 1 (thread per particle): push (optional), then the 1-D Esirkepov factors of the
-//     particle on a 4-slot WINDOW per axis -- for a 2nd-order shape and |move| < 1 cell the old and
-//     new weights together never span more than 4 of the 5 stencil slots
-//     (nix/esirkepov.hpp:240-275: the new weights are the old stencil shifted by -1/0/+1) --
-//     written to a per-warp staging buffer in shared memory;
-//   * phase 2 (thread per stencil point): each half-warp takes one staged particle; lane (a,b)
-//     owns the window points (a,b,*) and accumulates rho/Jx/Jy/Jz in REGISTERS with one FMA per
-//     value (the value is never materialised), exactly the sums of nix/esirkepov.hpp:154-237:
-//         rho[z][y][x]   += (q S1z[z] S1y[y])        * S1x[x]
-//         Jx [z][y][x+1] += W(y,z) * prefix_x DSx,   W = -q dx/dt ((S0y+DSy/2) S0z + (S0y/2+DSy/3) DSz)
-//         (Jy, Jz by cyclic permutation)
+//   * a block owns WARPS consecutive rows (fixed z, consecutive y) of RX cells; the E/B values all
+//     of its particles can touch ((RX+3) x (WARPS+3) x 4 points x 6 components, 14.8 KB) are staged
+//     ONCE in shared memory in the global layout, so every interpolation load is an LDS with an
+//     immediate offset (no address arithmetic, no L1/L2 latency);
+//   * each warp walks the cell-sorted particles of its row segment, 32 at a time:
+//       phase 1 (thread per particle): interpolate, push momentum and position, cell key +
+//         histogram, then the 1-D Esirkepov factors of the particle on a 4-slot WINDOW per axis --
+//         for a 2nd-order shape and |move| < 1 cell the old and new weights together never span
+//         more than 4 of the 5 stencil slots (nix/esirkepov.hpp:240-275: the new weights are the
+//         old stencil shifted by -1/0/+1) -- written as one 54-double record to shared memory;
+//       phase 2 (thread per stencil point): each half-warp takes one record; lane (a,b) owns the
+//         window points (a,b,*) and accumulates rho/Jx/Jy/Jz in REGISTERS with one FMA per value
+//         (the value is never materialised), exactly the sums of nix/esirkepov.hpp:154-237:
+//             rho[z][y][x]   += (S1z[z] S1y[y]) * q S1x[x]
+//             Jx [z][y][x+1] += W(y,z) * prefix_x DSx,  W = (S0y+DSy/2) S0z + (S0y/2+DSy/3) DSz
+//             (Jy, Jz by cyclic permutation; the factor -q dx/dt is folded into the prefix sums)
 //   * when the cell changes the 13 registers of a lane are added -- plain loads/stores, the lanes
 //     own distinct points -- into the warp's PRIVATE (RX+4) x 5 x 5 x 4 tile in shared memory;
-//   * at the end of the row segment the tile goes to global uj with one fp64 reduction per tile
-//     value (about 2.3 per particle at 64 ppc instead of ~170).
+//   * at the end of the row segment the tile goes to global uj with one fp64 reduction per non-zero
+//     tile value (about 2.3 per particle at 64 ppc instead of ~170).
 //
 // The few particles whose new weights fall left of the window (cell shift -1) use the same code
 // with a window that starts one slot lower and are flushed individually.  Results differ from the
@@ -35,38 +39,40 @@ namespace picnix
 namespace rowdep
 {
 
-constexpr int RX       = 8;               // cells per row segment
-constexpr int XS       = RX + 4;          // tile extent in x (stencil reaches -2..+2)
-constexpr int SY       = XS * 4 + 1;      // tile stride of y in doubles   (== 1 mod 16)
-constexpr int SZ       = 5 * SY + 15;     // tile stride of z in doubles   (== 4 mod 16)
-constexpr int TILE     = 5 * SZ;          // doubles per warp tile
-constexpr int NSTG     = 53;              // staged doubles per particle (odd: conflict-poor)
-constexpr int WARPS    = 4;               // warps per block
-constexpr int THREADS  = WARPS * 32;
+constexpr int RX      = 8;           // cells per row segment
+constexpr int WARPS   = 4;           // rows (consecutive y) per block
+constexpr int THREADS = WARPS * 32;
 
-// offsets inside a staged particle record
-constexpr int O_S1X = 0;   // S1x[4]            new x weights on the window
-constexpr int O_PX  = 4;   // Px[3]             -q dx/dt * prefix sums of DSx (window idx 1..3)
-constexpr int O_PY  = 7;   // Py[3]
-constexpr int O_PZ  = 10;  // Pz[3]
-constexpr int O_QS1Z = 13; // q * S1z[4]
-constexpr int O_S0Z = 17;  // S0z[4]
-constexpr int O_DSZ = 21;  // DSz[4]
-constexpr int O_S0Y = 25;  // S0y[4]
-constexpr int O_DSY = 29;  // DSy[4]
-constexpr int O_S1Y = 33;  // S1y[4]
-constexpr int O_AY  = 37;  // S0y + DSy/2
-constexpr int O_BY  = 41;  // S0y/2 + DSy/3
-constexpr int O_AX  = 45;  // S0x + DSx/2
-constexpr int O_BX  = 49;  // S0x/2 + DSx/3
+// field tile: points x in [jx0-1, jx0+RX+1], y in [jy0-1, jy0+WARPS+1], z in [jz-1, jz+2]
+constexpr int FX    = RX + 3;
+constexpr int FY    = WARPS + 3;
+constexpr int FZ    = 4;
+constexpr int FROW  = FX * 6;        // doubles per (z, y) row, global layout [x][6]
+constexpr int FTILE = FZ * FY * FROW;
+
+// current tile of a warp
+constexpr int XS   = RX + 4;         // extent in x (stencil reaches -2..+2)
+constexpr int SY   = XS * 4 + 1;     // stride of y in doubles   (== 1 mod 16)
+constexpr int SZ   = 5 * SY + 15;    // stride of z in doubles   (== 4 mod 16)
+constexpr int TILE = 5 * SZ;
+
+// staged particle record: 54 doubles = 27 x 16 B (odd multiple: conflict-free 128-bit stores)
+constexpr int REC    = 54;
+constexpr int O_QS1X = 0;   // q * S1x[4]
+constexpr int O_P    = 4;   // Px[3], Py[3], Pz[3]: -q d/dt * prefix sums of DS (window idx 1..3), pad
+constexpr int O_A1   = 14;  // [a] -> (S1z[a], S0z[a])
+constexpr int O_A2   = 22;  // [a] -> (DSz[a], S0y[a])
+constexpr int O_B1   = 30;  // [b] -> (S1y[b], AY[b])     AY = S0y + DSy/2
+constexpr int O_B2   = 38;  // [b] -> (BY[b],  AX[b])     BY = S0y/2 + DSy/3, AX = S0x + DSx/2
+constexpr int O_C    = 46;  // [i] -> (DSy[i], BX[i])     BX = S0x/2 + DSx/3
 
 struct WarpSmem {
-  double stg[32 * NSTG];
+  double stg[32 * REC];
   double tile[TILE];
   int    info[32];
 };
 
-constexpr size_t SMEM_BYTES = sizeof(WarpSmem) * WARPS;
+constexpr size_t SMEM_BYTES = sizeof(double) * FTILE + sizeof(WarpSmem) * WARPS;
 
 // info word: bits 0..7 cell index inside the segment, bit 8/9/10 window offset x/y/z (1 = majority
 // window that starts at the old cell's slot 1), bit 11 valid
@@ -75,33 +81,29 @@ __device__ __forceinline__ int make_info(int jx, int wx, int wy, int wz)
   return jx | (wx << 8) | (wy << 9) | (wz << 10) | (1 << 11);
 }
 
-// One axis: old/new 2nd-order weights on the 4-slot window.  Returns false when the move cannot be
-// represented (shift beyond one cell), in which case the caller takes the generic path.
+// 2nd-order momentum-conserving shape for a normalised offset delta in [-1/2, 1/2]
+// (nix/primitives.hpp:266-278)
+__device__ __forceinline__ void shape2(double delta, double* s)
+{
+  const double w1 = 0.5 - delta;
+  const double w2 = 0.5 + delta;
+  s[0] = 0.50 * w1 * w1;
+  s[1] = 0.75 - delta * delta;
+  s[2] = 0.50 * w2 * w2;
+}
+
+// old/new weights of one axis on the 4-slot window; s0/s1 are the 3 weights around the old/new cell
 struct AxisFactors {
   double S0[4], S1[4], DS[4];
-  int    i0;  // old cell (relative to the chunk)
-  int    w;   // window offset: 1 = slots 1..4, 0 = slots 0..3
-  bool   ok;
+  int    w; // window offset: 1 = slots 1..4 of the 5-slot stencil, 0 = slots 0..3
 };
 
-__device__ __forceinline__ AxisFactors axis_factors(double x0, double x1, double xmin, double dx)
+__device__ __forceinline__ AxisFactors window_factors(const double* s0, const double* s1, int sh)
 {
-  AxisFactors  f;
-  const double rdx   = 1 / dx;
-  const double xgrid = xmin + 0.5 * dx;
-
-  f.i0 = digitize(x0, xmin, rdx);
-  double s0[3], s1[3];
-  shape_mc<2>(x0, xgrid + (double)f.i0 * dx, rdx, s0);
-  const int i1 = digitize(x1, xmin, rdx);
-  shape_mc<2>(x1, xgrid + (double)i1 * dx, rdx, s1);
-
-  const int sh = i1 - f.i0;
-  f.ok         = sh >= -1 && sh <= 1;
-  f.w          = sh < 0 ? 0 : 1;
-  const bool w1 = f.w == 1;
+  AxisFactors f;
+  f.w           = sh < 0 ? 0 : 1;
+  const bool w1 = sh >= 0;
   const bool up = sh > 0; // new weights one slot to the right inside the window
-
   f.S0[0] = w1 ? s0[0] : 0.0;
   f.S0[1] = w1 ? s0[1] : s0[0];
   f.S0[2] = w1 ? s0[2] : s0[1];
@@ -116,47 +118,38 @@ __device__ __forceinline__ AxisFactors axis_factors(double x0, double x1, double
   return f;
 }
 
-// phase 1: stage the factors of one particle (lane-private record)
+__device__ __forceinline__ void store2(double* p, double a, double b)
+{
+  *reinterpret_cast<double2*>(p) = make_double2(a, b);
+}
+
+// phase 1: stage the factors of one particle (lane-private record, 16-byte stores)
 __device__ __forceinline__ void stage_particle(double* __restrict__ rec, const AxisFactors& fx,
                                                const AxisFactors& fy, const AxisFactors& fz,
                                                double q, double dxdt, double dydt, double dzdt)
 {
   const double A = 1.0 / 2, B = 1.0 / 3;
   const double cx = -q * dxdt, cy = -q * dydt, cz = -q * dzdt;
-  double       p;
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-    rec[O_S1X + k] = fx.S1[k];
-  p = fx.DS[0];
-  rec[O_PX + 0] = cx * p;
-  p += fx.DS[1];
-  rec[O_PX + 1] = cx * p;
-  p += fx.DS[2];
-  rec[O_PX + 2] = cx * p;
-  p = fy.DS[0];
-  rec[O_PY + 0] = cy * p;
-  p += fy.DS[1];
-  rec[O_PY + 1] = cy * p;
-  p += fy.DS[2];
-  rec[O_PY + 2] = cy * p;
-  p = fz.DS[0];
-  rec[O_PZ + 0] = cz * p;
-  p += fz.DS[1];
-  rec[O_PZ + 1] = cz * p;
-  p += fz.DS[2];
-  rec[O_PZ + 2] = cz * p;
+
+  store2(rec + O_QS1X + 0, q * fx.S1[0], q * fx.S1[1]);
+  store2(rec + O_QS1X + 2, q * fx.S1[2], q * fx.S1[3]);
+
+  const double px0 = fx.DS[0], px1 = px0 + fx.DS[1], px2 = px1 + fx.DS[2];
+  const double py0 = fy.DS[0], py1 = py0 + fy.DS[1], py2 = py1 + fy.DS[2];
+  const double pz0 = fz.DS[0], pz1 = pz0 + fz.DS[1], pz2 = pz1 + fz.DS[2];
+  store2(rec + O_P + 0, cx * px0, cx * px1);
+  store2(rec + O_P + 2, cx * px2, cy * py0);
+  store2(rec + O_P + 4, cy * py1, cy * py2);
+  store2(rec + O_P + 6, cz * pz0, cz * pz1);
+  store2(rec + O_P + 8, cz * pz2, 0.0);
+
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    rec[O_QS1Z + k] = q * fz.S1[k];
-    rec[O_S0Z + k]  = fz.S0[k];
-    rec[O_DSZ + k]  = fz.DS[k];
-    rec[O_S0Y + k]  = fy.S0[k];
-    rec[O_DSY + k]  = fy.DS[k];
-    rec[O_S1Y + k]  = fy.S1[k];
-    rec[O_AY + k]   = fy.S0[k] + A * fy.DS[k];
-    rec[O_BY + k]   = A * fy.S0[k] + B * fy.DS[k];
-    rec[O_AX + k]   = fx.S0[k] + A * fx.DS[k];
-    rec[O_BX + k]   = A * fx.S0[k] + B * fx.DS[k];
+    store2(rec + O_A1 + 2 * k, fz.S1[k], fz.S0[k]);
+    store2(rec + O_A2 + 2 * k, fz.DS[k], fy.S0[k]);
+    store2(rec + O_B1 + 2 * k, fy.S1[k], fy.S0[k] + A * fy.DS[k]);
+    store2(rec + O_B2 + 2 * k, A * fy.S0[k] + B * fy.DS[k], fx.S0[k] + A * fx.DS[k]);
+    store2(rec + O_C + 2 * k, fy.DS[k], A * fx.S0[k] + B * fx.DS[k]);
   }
 }
 
@@ -174,24 +167,39 @@ struct Acc {
   }
 };
 
-// phase 2 body: contributions of one staged particle to the points owned by lane (a, b)
+// phase 2 body: contributions of one staged particle to the points owned by lane (a, b);
+// 13 16-byte shared loads, 7 + 13 fp64 operations
 __device__ __forceinline__ void accumulate(Acc& acc, const double* __restrict__ rec, int a, int b)
 {
-  const double c   = rec[O_QS1Z + a] * rec[O_S1Y + b];
-  const double s0z = rec[O_S0Z + a], dsz = rec[O_DSZ + a];
-  const double s0y = rec[O_S0Y + a], dsy = rec[O_DSY + a];
-  const double wyz = rec[O_AY + b] * s0z + rec[O_BY + b] * dsz; // (jz=a, jy=b)
-  const double wzx = rec[O_AX + b] * s0z + rec[O_BX + b] * dsz; // (jz=a, jx=b)
-  const double wxy = rec[O_AX + b] * s0y + rec[O_BX + b] * dsy; // (jy=a, jx=b)
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-    acc.rho[k] += c * rec[O_S1X + k];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    acc.jx[k] += wyz * rec[O_PX + k];
-    acc.jy[k] += wzx * rec[O_PY + k];
-    acc.jz[k] += wxy * rec[O_PZ + k];
-  }
+  const double2* r2 = reinterpret_cast<const double2*>(rec);
+  const double2  qa = r2[O_QS1X / 2 + 0], qb = r2[O_QS1X / 2 + 1];
+  const double2  p0 = r2[O_P / 2 + 0], p1 = r2[O_P / 2 + 1], p2 = r2[O_P / 2 + 2],
+                p3 = r2[O_P / 2 + 3], p4 = r2[O_P / 2 + 4];
+  const double2 a1 = r2[O_A1 / 2 + a]; // S1z[a], S0z[a]
+  const double2 a2 = r2[O_A2 / 2 + a]; // DSz[a], S0y[a]
+  const double2 ca = r2[O_C / 2 + a];  // DSy[a], -
+  const double2 b1 = r2[O_B1 / 2 + b]; // S1y[b], AY[b]
+  const double2 b2 = r2[O_B2 / 2 + b]; // BY[b],  AX[b]
+  const double2 cb = r2[O_C / 2 + b];  // -,      BX[b]
+
+  const double c   = a1.x * b1.x;
+  const double wyz = b1.y * a1.y + b2.x * a2.x; // AY[b] S0z[a] + BY[b] DSz[a]   (jz=a, jy=b)
+  const double wzx = b2.y * a1.y + cb.y * a2.x; // AX[b] S0z[a] + BX[b] DSz[a]   (jz=a, jx=b)
+  const double wxy = b2.y * a2.y + cb.y * ca.x; // AX[b] S0y[a] + BX[b] DSy[a]   (jy=a, jx=b)
+
+  acc.rho[0] += c * qa.x;
+  acc.rho[1] += c * qa.y;
+  acc.rho[2] += c * qb.x;
+  acc.rho[3] += c * qb.y;
+  acc.jx[0] += wyz * p0.x;
+  acc.jx[1] += wyz * p0.y;
+  acc.jx[2] += wyz * p1.x;
+  acc.jy[0] += wzx * p1.y;
+  acc.jy[1] += wzx * p2.x;
+  acc.jy[2] += wzx * p2.y;
+  acc.jz[0] += wxy * p3.x;
+  acc.jz[1] += wxy * p3.y;
+  acc.jz[2] += wxy * p4.x;
 }
 
 // add a lane's accumulators into the warp tile; (wz,wy,wx) window offset, jx cell in the segment
