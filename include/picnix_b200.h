@@ -206,10 +206,21 @@ int picnix_cuda_get_counters(const picnix_arena_t* arena, int64_t* kernel_launch
  * steps, and download the state back.  uf/uj/ff: [nchunk][...] concatenated; xu: AoS particles of
  * all (chunk, species) segments concatenated with `np_in[seg]` entries each and room for
  * `np_cap[seg]`; np_out receives the new counts.
+ *
+ * The call is a three-stream pipeline (copy-in / compute / copy-out, hostio.cu) and is bound by the
+ * PCIe link.  The buffers are used in place: pageable buffers are page-locked on first use
+ * (cudaHostRegister) and stay registered until the arena is destroyed, so pass the SAME arrays
+ * every step, or allocate them with picnix_cuda_host_alloc.  `uj` is an output only when
+ * nstep >= 1 (the deposit starts from zero, pic/engine/current.hpp:91).
  */
 int picnix_cuda_step_host(picnix_arena_t* arena, double delt, int32_t nstep, double* uf,
                           double* uj, double* ff, double* xu, const int32_t* np_in,
                           const int32_t* np_cap, int32_t* np_out);
+
+/* page-locked host memory for the arrays handed to picnix_cuda_step_host / upload / download
+ * (an xt::xtensor can adopt it through xt::adapt); PICNIX_ERR_NODEVICE without a CUDA device */
+int picnix_cuda_host_alloc(void** ptr, int64_t bytes);
+int picnix_cuda_host_free(void* ptr);
 
 #ifdef __cplusplus
 }

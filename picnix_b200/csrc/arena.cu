@@ -6,6 +6,7 @@
 // neighbour tables follow nix::ChunkVector::set_neighbors (nix/chunkvector.hpp:56-81) and the
 // particle containers follow nix::XtensorParticle::allocate (nix/xtensor_particle.hpp:49-65).
 #include "arena.hpp"
+#include "transpose_kernels.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -47,33 +48,6 @@ static void dev_free(T*& ptr)
     cudaFree(ptr);
     ptr = nullptr;
   }
-}
-
-//
-// AoS <-> SoA transposes at the host boundary (the reference's particle array is [Np][7])
-//
-__global__ void aos_to_soa_kernel(const double* __restrict__ aos, double* __restrict__ soa,
-                                  int64_t off, int64_t pcap, int n)
-{
-  // one thread per (particle, component) of the staged AoS block: coalesced reads, strided writes
-  // that still fall in 7 contiguous runs per warp
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)n * NC)
-    return;
-  int ip            = (int)(i / NC);
-  int ic            = (int)(i - (int64_t)ip * NC);
-  soa[ic * pcap + off + ip] = aos[i];
-}
-
-__global__ void soa_to_aos_kernel(const double* __restrict__ soa, double* __restrict__ aos,
-                                  int64_t off, int64_t pcap, int n)
-{
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)n * NC)
-    return;
-  int ip = (int)(i / NC);
-  int ic = (int)(i - (int64_t)ip * NC);
-  aos[i] = soa[ic * pcap + off + ip];
 }
 
 static int ensure_stage(picnix_arena* a, int64_t elems)
@@ -150,35 +124,6 @@ int download_particles(picnix_arena* a, int ichunk, int is, int which, int n, do
   PICNIX_CUDA(a, cudaStreamSynchronize(a->stream));
   std::memcpy(aos, a->h_stage, elems * sizeof(double));
   return PICNIX_OK;
-}
-
-//
-// ff: host layout [cell][3][6] (reference) <-> device layout [cell][3][3]
-//
-__global__ void ff_expand_kernel(const double* __restrict__ dev, double* __restrict__ host_layout,
-                                 int64_t ncell)
-{
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ncell * 18)
-    return;
-  int64_t cell = i / 18;
-  int     r    = (int)(i - cell * 18);
-  int     t    = r / 6;
-  int     k    = r - t * 6;
-  host_layout[i] = k < 3 ? dev[cell * 9 + t * 3 + k] : 0.0;
-}
-
-__global__ void ff_compact_kernel(const double* __restrict__ host_layout, double* __restrict__ dev,
-                                  int64_t ncell)
-{
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ncell * 9)
-    return;
-  int64_t cell = i / 9;
-  int     r    = (int)(i - cell * 9);
-  int     t    = r / 3;
-  int     k    = r - t * 3;
-  dev[i]       = host_layout[cell * 18 + t * 6 + k];
 }
 
 static int field_info(picnix_arena* a, int ichunk, int which, double** dptr, int64_t* elems)
@@ -496,6 +441,7 @@ int picnix_cuda_arena_destroy(picnix_arena_t* a)
   dev_free(a->d.far_count);
   dev_free(a->d.far_rec);
   dev_free(a->d_reduce);
+  hostio_destroy(a);
   dev_free(a->d_stage);
   dev_free(a->d_slot_peer);
   dev_free(a->d_slot_dst);

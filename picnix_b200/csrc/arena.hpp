@@ -99,6 +99,11 @@ struct PeerPlan {
 
 } // namespace picnix
 
+namespace picnix
+{
+struct HostIO; // hostio.cu: streams, slabs and events of the pipelined host-buffer step
+}
+
 // The opaque handle of the C ABI.
 struct picnix_arena {
   picnix_config_t        cfg;
@@ -130,6 +135,7 @@ struct picnix_arena {
   double*                h_stage     = nullptr; // pinned staging for AoS<->SoA transfers
   double*                d_stage     = nullptr;
   int64_t                stage_elems = 0;
+  picnix::HostIO*        hostio      = nullptr;
   bool                   particles_allocated = false;
   bool                   pindex_valid = false;  // pindex matches the particle order (after a sort)
   bool                   force_generic = false; // testing: bypass the tiled kernels
@@ -185,6 +191,10 @@ int launch_sort(picnix_arena* a, int c0, int cn);
 
 int launch_halo_begin(picnix_arena* a, int mode);
 int launch_halo_end(picnix_arena* a, int mode);
+
+void hostio_destroy(picnix_arena* a);
+int  step_host_pipelined(picnix_arena* a, double delt, int nstep, double* uf, double* uj, double* ff,
+                         double* xu, const int32_t* np_in, const int32_t* np_cap, int32_t* np_out);
 
 int upload_particles(picnix_arena* a, int ichunk, int is, const double* aos, int np);
 int download_particles(picnix_arena* a, int ichunk, int is, int which, int n, double* aos);

@@ -157,54 +157,12 @@ int picnix_cuda_step_host(picnix_arena_t* a, double delt, int32_t nstep, double*
       np_in == nullptr || np_cap == nullptr || np_out == nullptr)
     return PICNIX_ERR_INVALID;
 
-  const Geom&   g     = a->g;
-  const int64_t ncell = g.Ng;
-  int           status;
-
-  if (!a->particles_allocated) {
-    if ((status = picnix_cuda_set_particle_capacity(a, np_cap)) != PICNIX_OK)
-      return status;
-  }
-
-  int64_t poff = 0;
-  for (int ic = 0; ic < g.nchunk; ic++) {
-    if ((status = picnix_cuda_upload_field(a, ic, PICNIX_FIELD_UF, uf + ic * ncell * 6)) != 0)
-      return status;
-    if ((status = picnix_cuda_upload_field(a, ic, PICNIX_FIELD_UJ, uj + ic * ncell * 4)) != 0)
-      return status;
-    if ((status = picnix_cuda_upload_field(a, ic, PICNIX_FIELD_FF, ff + ic * ncell * 18)) != 0)
-      return status;
-    for (int is = 0; is < g.Ns; is++) {
-      int seg = ic * g.Ns + is;
-      if ((status = upload_particles(a, ic, is, xu + poff * NC, np_in[seg])) != PICNIX_OK)
-        return status;
-      poff += np_cap[seg];
-    }
-  }
-
-  if ((status = picnix_cuda_step(a, delt, nstep)) != PICNIX_OK)
-    return status;
-  if ((status = picnix_cuda_get_np(a, np_out)) != PICNIX_OK)
-    return status;
-
-  poff = 0;
-  for (int ic = 0; ic < g.nchunk; ic++) {
-    if ((status = picnix_cuda_download_field(a, ic, PICNIX_FIELD_UF, uf + ic * ncell * 6)) != 0)
-      return status;
-    if ((status = picnix_cuda_download_field(a, ic, PICNIX_FIELD_UJ, uj + ic * ncell * 4)) != 0)
-      return status;
-    if ((status = picnix_cuda_download_field(a, ic, PICNIX_FIELD_FF, ff + ic * ncell * 18)) != 0)
-      return status;
-    for (int is = 0; is < g.Ns; is++) {
-      int seg = ic * g.Ns + is;
-      if (np_out[seg] > np_cap[seg])
-        return fail(a, PICNIX_ERR_OVERFLOW, "host particle buffer too small for the new count");
-      if ((status = download_particles(a, ic, is, 0, np_out[seg], xu + poff * NC)) != PICNIX_OK)
-        return status;
-      poff += np_cap[seg];
-    }
-  }
-  return picnix_cuda_synchronize(a);
+  if (nstep < 0)
+    return fail(a, PICNIX_ERR_INVALID, "nstep must be >= 0");
+  if (a->cfg.nrank != 1)
+    return fail(a, PICNIX_ERR_INVALID, "picnix_cuda_step_host needs nrank == 1");
+  // pipelined transfer + step, hostio.cu
+  return step_host_pipelined(a, delt, nstep, uf, uj, ff, xu, np_in, np_cap, np_out);
 }
 
 } // extern "C"

@@ -156,43 +156,23 @@ class DistributedSim(CudaSim):
         import torch
 
         assert self.world == 1
-        Ns, nchunk, ncell = self.Ns, self.nchunk, self.Ng
-        np_now = self.get_np_all().reshape(-1).astype(np.int32)
-        caps = np.array([int(n * (1 + self.cfg.buffer_ratio)) for n in np_now], dtype=np.int32)
-        caps = ((caps + 128) // 128) * 128
-
-        def pinned(n):
-            return torch.empty(int(n), dtype=torch.float64, pin_memory=True).numpy()
-
-        uf, uj, ff = pinned(nchunk * ncell * 6), pinned(nchunk * ncell * 4), pinned(nchunk * ncell * 18)
-        xu = pinned(int(caps.sum()) * 7)
-        # current device state -> host arrays (outside the timed region)
-        off = 0
-        for ic in range(nchunk):
-            uf[ic * ncell * 6:(ic + 1) * ncell * 6] = self.get_field(ic, capi.FIELD_UF).reshape(-1)
-            uj[ic * ncell * 4:(ic + 1) * ncell * 4] = self.get_field(ic, capi.FIELD_UJ).reshape(-1)
-            ff[ic * ncell * 18:(ic + 1) * ncell * 18] = self.get_field(ic, capi.FIELD_FF).reshape(-1)
-            for isp in range(Ns):
-                seg = ic * Ns + isp
-                n = int(np_now[seg])
-                xu[off * 7:(off + n) * 7] = self.get_particles(ic, isp, 0, n).reshape(-1)
-                off += int(caps[seg])
-        np_in = np_now.copy()
-        np_out = np.zeros_like(np_in)
+        st = self.host_state(pinned=True)  # outside the timed region
+        np_now = st["np"].copy()
+        fields = st["uf"].nbytes + st["uj"].nbytes + st["ff"].nbytes
         h2d = d2h = 0
+        self.step_host(st, dt, 1)  # untimed: allocates the slabs and streams of the pipeline
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(nstep):
-            self._check(self.lib.picnix_cuda_step_host(self.h, dt, 1, uf, uj, ff, xu, np_in, caps, np_out))
-            h2d += (uf.nbytes + uj.nbytes + ff.nbytes) + int(np_in.sum()) * 56
-            d2h += (uf.nbytes + uj.nbytes + ff.nbytes) + int(np_out.sum()) * 56
-            np_in, np_out = np_out.copy(), np_in
+            h2d += fields - st["uj"].nbytes + int(st["np"].sum()) * 56  # uj is an output only
+            self.step_host(st, dt, 1)
+            d2h += fields + int(st["np"].sum()) * 56
         torch.cuda.synchronize()
         elapsed = time.perf_counter() - t0
         return {
             "value": float(np_now.sum()) * nstep / elapsed, "unit": "particle-steps/s",
             "h2d_bytes_per_step": h2d // nstep, "d2h_bytes_per_step": d2h // nstep, "steps": nstep,
             "ms_per_step": 1e3 * elapsed / nstep,
-            "api": "picnix_cuda_step_host: reference-layout host arrays (uf, uj, ff, AoS particles) in and out "
-                   "every step",
+            "api": "picnix_cuda_step_host: pinned reference-layout host arrays (uf, ff, AoS particles in; uf, uj, "
+                   "ff, AoS particles out) every step, three-stream copy/transposition pipeline",
         }

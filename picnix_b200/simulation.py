@@ -228,6 +228,51 @@ class CudaSim:
         self.commit()
         self._check(self.lib.picnix_cuda_step(self.h, dt, nstep))
 
+    # -- host-buffer step (what a host-resident PicChunk would call) --------------------------
+    def host_state(self, pinned=True):
+        """Current device state as HOST arrays in the reference's layouts (uf, uj, ff[..][3][6], AoS
+        particles with `caps[seg]` slots per (chunk, species) segment) -- the argument of step_host."""
+        self.commit()
+        Ns, nchunk, ncell = self.Ns, self.nchunk, self.Ng
+
+        def alloc(n):
+            if pinned:
+                import torch
+
+                return torch.zeros(int(n), dtype=torch.float64, pin_memory=True).numpy()
+            return np.zeros(int(n), dtype=np.float64)
+
+        np_now = self.get_np_all().reshape(-1).astype(np.int32)
+        caps = np.array([int(n * (1 + self.cfg.buffer_ratio)) for n in np_now], dtype=np.int32)
+        caps = ((caps + 128) // 128) * 128
+        st = {"uf": alloc(nchunk * ncell * 6), "uj": alloc(nchunk * ncell * 4), "ff": alloc(nchunk * ncell * 18),
+              "xu": alloc(int(caps.sum()) * 7), "np": np_now.copy(), "caps": caps}
+        off = 0
+        for ic in range(nchunk):
+            st["uf"][ic * ncell * 6:(ic + 1) * ncell * 6] = self.get_field(ic, capi.FIELD_UF).reshape(-1)
+            st["uj"][ic * ncell * 4:(ic + 1) * ncell * 4] = self.get_field(ic, capi.FIELD_UJ).reshape(-1)
+            st["ff"][ic * ncell * 18:(ic + 1) * ncell * 18] = self.get_field(ic, capi.FIELD_FF).reshape(-1)
+            for isp in range(Ns):
+                seg = ic * Ns + isp
+                n = int(np_now[seg])
+                st["xu"][off * 7:(off + n) * 7] = self.get_particles(ic, isp, 0, n).reshape(-1)
+                off += int(caps[seg])
+        return st
+
+    def step_host(self, st, dt, nstep=1):
+        """picnix_cuda_step_host: host arrays in, `nstep` steps on the device, host arrays out."""
+        np_out = np.zeros_like(st["np"])
+        self._check(self.lib.picnix_cuda_step_host(self.h, dt, nstep, st["uf"], st["uj"], st["ff"], st["xu"],
+                                                   st["np"], st["caps"], np_out))
+        st["np"] = np_out
+        return st
+
+    @staticmethod
+    def host_particles(st, Ns, ic, isp):
+        seg = ic * Ns + isp
+        off = int(st["caps"][:seg].sum())
+        return st["xu"][off * 7:(off + int(st["np"][seg])) * 7].reshape(-1, 7)
+
     def get_diverror(self):
         e = np.zeros(self.nchunk)
         b = np.zeros(self.nchunk)
