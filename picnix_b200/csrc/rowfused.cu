@@ -99,8 +99,12 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
   const int      lane = threadIdx.x & 31;
   const int      warp = threadIdx.x >> 5;
   const int      half = lane >> 4;
-  const int      a    = (lane >> 2) & 3;
-  const int      b    = lane & 3;
+  // (a, b) of a lane inside its half-warp.  A shared-memory wavefront serves each aligned group of
+  // 4 lanes with at most two distinct addresses in the patterns XXYY / XYXY (measured,
+  // tools/micro/lds_patterns.cu), so both the a-indexed and the b-indexed record loads of phase 2
+  // must take only two values per quad: bit 1 of the lane is the low bit of a, bit 0 the low bit of b.
+  const int      a    = ((lane >> 2) & 2) | ((lane >> 1) & 1);
+  const int      b    = ((lane >> 1) & 2) | (lane & 1);
   const unsigned FULL = 0xffffffffu;
   WarpSmem*      ws   = wsm + warp;
 
@@ -165,6 +169,19 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
     acc.clear();
     int curinfo = -1; // info word of the cell the accumulators belong to (-1: none)
 
+    // the six phase-space components of the NEXT batch are requested before phase 2 of the current
+    // one, so their HBM latency is hidden behind the accumulation loop
+    double pfx = 0, pfy = 0, pfz = 0, pfux = 0, pfuy = 0, pfuz = 0;
+    if (FUSED && pb + lane < pe) {
+      const int64_t i = off + pb + lane;
+      pfx  = d.xu[0 * d.pcap + i];
+      pfy  = d.xu[1 * d.pcap + i];
+      pfz  = d.xu[2 * d.pcap + i];
+      pfux = d.xu[3 * d.pcap + i];
+      pfuy = d.xu[4 * d.pcap + i];
+      pfuz = d.xu[5 * d.pcap + i];
+    }
+
     for (int base = pb; base < pe; base += 32) {
       const int n = min(32, pe - base);
 
@@ -176,12 +193,12 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
         double        s0x[3], s0y[3], s0z[3];
         int           cx; // old cell in x, relative to the chunk
         if (FUSED) {
-          x0        = d.xu[0 * d.pcap + i];
-          y0        = d.xu[1 * d.pcap + i];
-          z0        = d.xu[2 * d.pcap + i];
-          double ux = d.xu[3 * d.pcap + i];
-          double uy = d.xu[4 * d.pcap + i];
-          double uz = d.xu[5 * d.pcap + i];
+          x0        = pfx;
+          y0        = pfy;
+          z0        = pfz;
+          double ux = pfux;
+          double uy = pfuy;
+          double uz = pfuz;
 
           // weights on the centre grid (MC or WT) and on the edge grid (MC); the particle is in
           // row (jz, jy) by construction of the sort, only its x cell has to be found
@@ -280,6 +297,15 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
         }
       }
       ws->info[lane] = inf;
+      if (FUSED && base + 32 + lane < pe) {
+        const int64_t i = off + base + 32 + lane;
+        pfx  = d.xu[0 * d.pcap + i];
+        pfy  = d.xu[1 * d.pcap + i];
+        pfz  = d.xu[2 * d.pcap + i];
+        pfux = d.xu[3 * d.pcap + i];
+        pfuy = d.xu[4 * d.pcap + i];
+        pfuz = d.xu[5 * d.pcap + i];
+      }
       __syncwarp();
 
       // ---------------- phase 2: one staged particle per half-warp ----------------

@@ -76,6 +76,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(Geom g, DevPtrs d, i
   }
 }
 
+// One thread per particle.  Cell-ordered input means the lanes of a warp hold a handful of distinct
+// keys, so the cursor is bumped once per distinct key and warp (match.any + one leader atomic)
+// instead of once per particle: ~30x fewer same-address L2 atomics at 32 particles per cell.
 __global__ void __launch_bounds__(SCATTER_THREADS)
 scatter_kernel(Geom g, DevPtrs d, int seg0, int blocks_per_seg)
 {
@@ -83,17 +86,26 @@ scatter_kernel(Geom g, DevPtrs d, int seg0, int blocks_per_seg)
   const int b    = blockIdx.x - lseg * blocks_per_seg;
   const int seg  = seg0 + lseg;
   const int ip   = b * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   // own particles plus the migrants appended behind them during this step
   const int n    = min(d.np[seg] + d.ntail[seg], d.seg_cap[seg]);
-  if (ip >= n)
-    return;
+  if (b * (int)blockDim.x + (int)(threadIdx.x & ~31u) >= n)
+    return; // whole warp beyond the segment
 
   const int64_t off = d.seg_off[seg];
-  const int     key = d.gindex[off + ip];
-  if (key >= g.Ng)
-    return; // left the chunk: discarded (nix/xtensor_particle.hpp:319-320)
+  // particles that left the chunk (key == Ng) are discarded (nix/xtensor_particle.hpp:319-320)
+  const int  key  = ip < n ? d.gindex[off + ip] : g.Ng;
+  const bool keep = key < g.Ng;
 
-  const int dst = atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, 1);
+  const unsigned peers  = __match_any_sync(0xffffffffu, key);
+  const int      leader = __ffs(peers) - 1;
+  int            base   = 0;
+  if (keep && lane == leader)
+    base = atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (!keep)
+    return;
+  const int dst = base + __popc(peers & ((1u << lane) - 1u));
 #pragma unroll
   for (int k = 0; k < NC; k++)
     d.xv[k * d.pcap + off + dst] = d.xu[k * d.pcap + off + ip];
