@@ -75,6 +75,7 @@ int upload_particles(picnix_arena* a, int ichunk, int is, const double* aos, int
     return fail(a, PICNIX_ERR_OVERFLOW, "upload_particles: np exceeds segment capacity");
 
   a->pindex_valid = false; // the new particles are not cell-ordered until the next sort
+  a->leave_list_valid = false;
   int64_t elems = (int64_t)np * NC;
   if (np > 0) {
     int status = ensure_stage(a, elems);
@@ -440,6 +441,8 @@ int picnix_cuda_arena_destroy(picnix_arena_t* a)
   dev_free(a->d.errflag);
   dev_free(a->d.far_count);
   dev_free(a->d.far_rec);
+  dev_free(a->d.leave_count);
+  dev_free(a->d.leave_idx);
   dev_free(a->d_reduce);
   hostio_destroy(a);
   dev_free(a->d_stage);
@@ -557,6 +560,9 @@ int picnix_cuda_set_particle_capacity(picnix_arena_t* a, const int32_t* np_alloc
   dev_free(a->d.xu);
   dev_free(a->d.xv);
   dev_free(a->d.gindex);
+  dev_free(a->d.leave_count);
+  dev_free(a->d.leave_idx);
+  a->leave_list_valid = false;
 
   int64_t total = 0;
   for (int s = 0; s < a->nseg; s++) {
@@ -576,6 +582,13 @@ int picnix_cuda_set_particle_capacity(picnix_arena_t* a, const int32_t* np_alloc
   if ((status = dev_alloc(a, &a->d.xv, (size_t)total * NC)) != PICNIX_OK)
     return status;
   if ((status = dev_alloc(a, &a->d.gindex, (size_t)total)) != PICNIX_OK)
+    return status;
+  // a quarter of the population leaving in one step is far beyond any Courant-limited run; the
+  // migration falls back to scanning the keys if the list overflows
+  a->d.leave_cap = (int)std::min<int64_t>(std::max<int64_t>(4096, total / 4), 1 << 30);
+  if ((status = dev_alloc(a, &a->d.leave_count, 1)) != PICNIX_OK)
+    return status;
+  if ((status = dev_alloc(a, &a->d.leave_idx, (size_t)a->d.leave_cap, false)) != PICNIX_OK)
     return status;
   PICNIX_CUDA(a, cudaMemcpy(a->d.seg_off, a->seg_off.data(), a->nseg * sizeof(int64_t),
                             cudaMemcpyHostToDevice));

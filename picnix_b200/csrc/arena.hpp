@@ -73,6 +73,11 @@ struct DevPtrs {
   int*     far_count; // [1] particles that moved more than one cell in the row kernel
   double*  far_rec;   // [far_cap][8] x0,y0,z0,x1,y1,z1,q,chunk: deposited by a follow-up kernel
   int      far_cap;
+  // particles that left their chunk in the fused push (key == Ng), as (segment << 40 | slot):
+  // the migration visits this list instead of scanning every key again
+  int*     leave_count; // [1]
+  int64_t* leave_idx;   // [leave_cap]
+  int      leave_cap;
 };
 
 struct PeerPlan {
@@ -138,6 +143,7 @@ struct picnix_arena {
   picnix::HostIO*        hostio      = nullptr;
   bool                   particles_allocated = false;
   bool                   pindex_valid = false;  // pindex matches the particle order (after a sort)
+  bool                   leave_list_valid = false; // DevPtrs::leave_idx describes the current keys
   bool                   force_generic = false; // testing: bypass the tiled kernels
   int64_t                kernel_launches = 0;
   int64_t                particle_pushes = 0;

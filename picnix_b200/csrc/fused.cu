@@ -71,6 +71,8 @@ fused_generic_kernel(Geom g, DevPtrs d, int c0, int blocks_per_seg, double delt)
   const int key = cell_key(g, lim, x1, y1, z1);
   d.gindex[i]   = key;
   atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, 1);
+  if (key == g.Ng)
+    note_leaver(d, seg, i);
 
   double*   uj = d.uj + (int64_t)chunk * g.Ng * 4;
   int       bz = 0, by = 0, bx = 0;
@@ -150,6 +152,10 @@ int launch_push_deposit_fused(picnix_arena* a, int c0, int cn, double delt)
                                  (size_t)cn * g.Ng * 4 * sizeof(double), a->stream));
   PICNIX_CUDA(a, cudaMemsetAsync(a->d.pcount + (int64_t)c0 * g.Ns * nbin, 0,
                                  (size_t)cn * g.Ns * nbin * sizeof(int), a->stream));
+
+  // the kernels below list the particles that leave their chunk for the migration
+  PICNIX_CUDA(a, cudaMemsetAsync(a->d.leave_count, 0, sizeof(int), a->stream));
+  a->leave_list_valid = (c0 == 0 && cn == g.nchunk);
 
   if (row_kernel_applies(a))
     return launch_row_fused(a, c0, cn, delt);

@@ -251,18 +251,10 @@ __device__ __forceinline__ void append_particle(const Geom& g, const DevPtrs& d,
   atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, 1);
 }
 
-__global__ void __launch_bounds__(HALO_THREADS)
-migrate_kernel(Geom g, DevPtrs d, MigrateTables tab, int blocks_per_seg)
+// send one particle that left (chunk, species) to the neighbour its position points at
+__device__ __forceinline__ void migrate_particle(const Geom& g, const DevPtrs& d,
+                                                 const MigrateTables& tab, int seg, int64_t i)
 {
-  const int seg   = blockIdx.x / blocks_per_seg;
-  const int b     = blockIdx.x - seg * blocks_per_seg;
-  const int ip    = b * blockDim.x + threadIdx.x;
-  if (ip >= d.np[seg])
-    return;
-  const int64_t i = d.seg_off[seg] + ip;
-  if (d.gindex[i] != g.Ng)
-    return; // still inside its chunk
-
   const int chunk = seg / g.Ns;
   const int is    = seg - chunk * g.Ns;
   double    p[NC];
@@ -293,6 +285,42 @@ migrate_kernel(Geom g, DevPtrs d, MigrateTables tab, int blocks_per_seg)
     out[7]   = *reinterpret_cast<double*>(&tag);
   }
   // NB_NONE: open boundary, the particle is simply dropped by the sort (MPI_PROC_NULL send)
+}
+
+// Leavers listed by the fused push kernel: one thread per list entry (about 1 % of the particles).
+// An overflowed list is left to the scan kernel below.
+__global__ void __launch_bounds__(HALO_THREADS)
+migrate_list_kernel(Geom g, DevPtrs d, MigrateTables tab)
+{
+  const int n = *d.leave_count;
+  if (n > d.leave_cap)
+    return;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int64_t e = d.leave_idx[k];
+    migrate_particle(g, d, tab, (int)(e >> 40), e & (((int64_t)1 << 40) - 1));
+  }
+}
+
+// Scan of all keys (XtensorHaloParticle3D::pre_pack looks at every particle too,
+// nix/xtensor_halo3d.hpp:192-260).  Used when no leaver list describes the current keys
+// (use_list == 0), and as the fallback of an overflowed list (use_list == 1).
+__global__ void __launch_bounds__(HALO_THREADS)
+migrate_kernel(Geom g, DevPtrs d, MigrateTables tab, int stride, int use_list)
+{
+  if (use_list && *d.leave_count <= d.leave_cap)
+    return;
+  const int64_t total = (int64_t)g.nchunk * g.Ns * stride;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int seg = (int)(idx / stride);
+    const int ip  = (int)(idx - (int64_t)seg * stride);
+    if (ip >= d.np[seg])
+      continue;
+    const int64_t i = d.seg_off[seg] + ip;
+    if (d.gindex[i] != g.Ng)
+      continue; // still inside its chunk
+    migrate_particle(g, d, tab, seg, i);
+  }
 }
 
 __global__ void __launch_bounds__(HALO_THREADS)
@@ -541,12 +569,21 @@ int launch_halo_begin(picnix_arena* a, int mode)
     int maxcap = 0;
     for (int s = 0; s < a->nseg; s++)
       maxcap = std::max(maxcap, a->seg_cap[s]);
-    int bps = (maxcap + HALO_THREADS - 1) / HALO_THREADS;
-    if (bps > 0) {
+    if (maxcap > 0) {
       MigrateTables tab{a->d_slot_peer, a->d_psend_ptrs, a->d_psend_cnts, a->d_psend_caps,
                         a->d_slot_dst};
-      migrate_kernel<<<bps * a->nseg, HALO_THREADS, 0, a->stream>>>(g, a->d, tab, bps);
+      const int     use_list = a->leave_list_valid ? 1 : 0;
+      const int64_t total    = (int64_t)a->nseg * maxcap;
+      if (use_list) {
+        migrate_list_kernel<<<148 * 4, HALO_THREADS, 0, a->stream>>>(g, a->d, tab);
+        a->kernel_launches++;
+      }
+      // grid-stride: a resident grid when it is only the overflow fallback of the list
+      const int64_t want   = (total + HALO_THREADS - 1) / HALO_THREADS;
+      const int     blocks = (int)std::min<int64_t>(want, use_list ? 148 * 8 : 148 * 64);
+      migrate_kernel<<<blocks, HALO_THREADS, 0, a->stream>>>(g, a->d, tab, maxcap, use_list);
       a->kernel_launches++;
+      a->leave_list_valid = false; // appended migrants are not on the list
     }
     // exact send sizes must be known to the host before the transfer (like MPI_Get_count)
     for (auto& p : a->peers) {

@@ -261,6 +261,7 @@ int launch_push_position(picnix_arena* a, int c0, int cn, double delt)
   const int64_t nbin = a->g.Ng + 1;
   PICNIX_CUDA(a, cudaMemsetAsync(a->d.pcount + (int64_t)c0 * a->g.Ns * nbin, 0,
                                  (size_t)cn * a->g.Ns * nbin * sizeof(int), a->stream));
+  a->leave_list_valid = false;
   position_kernel<<<bps * cn * a->g.Ns, PTHREADS, 0, a->stream>>>(a->g, a->d, c0, bps, delt);
   a->kernel_launches++;
   return check_cuda(a, cudaGetLastError(), "push_position");
@@ -277,6 +278,7 @@ int launch_count(picnix_arena* a, int c0, int cn)
   const int64_t nbin = a->g.Ng + 1;
   PICNIX_CUDA(a, cudaMemsetAsync(a->d.pcount + (int64_t)c0 * a->g.Ns * nbin, 0,
                                  (size_t)cn * a->g.Ns * nbin * sizeof(int), a->stream));
+  a->leave_list_valid = false;
   count_kernel<<<bps * cn * a->g.Ns, PTHREADS, 0, a->stream>>>(a->g, a->d, c0, bps);
   a->kernel_launches++;
   return check_cuda(a, cudaGetLastError(), "count");

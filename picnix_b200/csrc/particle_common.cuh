@@ -19,6 +19,14 @@
 namespace picnix
 {
 
+// remember a particle that left its chunk (key == Ng) for the migration kernel
+__device__ __forceinline__ void note_leaver(const DevPtrs& d, int seg, int64_t slot)
+{
+  const int k = atomicAdd(d.leave_count, 1);
+  if (k < d.leave_cap)
+    d.leave_idx[k] = ((int64_t)seg << 40) | slot;
+}
+
 __device__ __forceinline__ int digitize(double x, double xmin, double rdx)
 {
   return (int)floor((x - xmin) * rdx);

@@ -48,13 +48,27 @@ constexpr int FX    = RX + 3;
 constexpr int FY    = WARPS + 3;
 constexpr int FZ    = 4;
 constexpr int FROW  = FX * 6;        // doubles per (z, y) row, global layout [x][6]
-constexpr int FTILE = FZ * FY * FROW;
+// z-slab stride.  Lanes of a warp read the same stencil point shifted by hx (12 words), hy (2*FROW
+// = 132 = 4 mod 32 words) and hz (one slab); with the natural slab of FY*FROW doubles (28 mod 32
+// words) the (hy, hz) = (1, 1) and (0, 0) variants of Bx fall on the same bank.  +6 doubles makes the
+// slab 8 mod 32 words: {0,4,8,12} + {0,12} are all distinct bank pairs.
+constexpr int FSLAB = FY * FROW + 6;
+constexpr int FTILE = FZ * FSLAB;
 
-// current tile of a warp
+// current tile of a warp: one array per component, [z][y][x] with x contiguous.  The strides make
+// every read-modify-write of flush() conflict free for the 16 lanes (a, b) of a half-warp (two
+// words per lane, so a*Sa + b*Sb must be distinct mod 16):
+//   rho, Jx: a -> z, b -> y   SZR = 65 (1 mod 16),  SYT = 12:  a + 12 b
+//   Jy     : a -> z, b -> x   SZT = 60 (12 mod 16), x = 1   :  12 a + b
+//   Jz     : a -> y, b -> x   SYT = 12,             x = 1   :  12 a + b
 constexpr int XS   = RX + 4;         // extent in x (stencil reaches -2..+2)
-constexpr int SY   = XS * 4 + 1;     // stride of y in doubles   (== 1 mod 16)
-constexpr int SZ   = 5 * SY + 15;    // stride of z in doubles   (== 4 mod 16)
-constexpr int TILE = 5 * SZ;
+constexpr int SYT  = XS;             // stride of y, all components
+constexpr int SZR  = 5 * SYT + 5;    // stride of z for rho and Jx
+constexpr int SZT  = 5 * SYT;        // stride of z for Jy and Jz
+constexpr int T_RHO = 0, T_JX = 5 * SZR, T_JY = 10 * SZR, T_JZ = 10 * SZR + 5 * SZT;
+constexpr int TILE = 10 * SZR + 10 * SZT;
+__host__ __device__ constexpr int tile_base(int comp) { return comp == 0 ? T_RHO : (comp == 1 ? T_JX : (comp == 2 ? T_JY : T_JZ)); }
+__host__ __device__ constexpr int tile_sz(int comp) { return comp < 2 ? SZR : SZT; }
 
 // staged particle record: 54 doubles = 27 x 16 B (odd multiple: conflict-free 128-bit stores)
 constexpr int REC    = 54;
@@ -207,23 +221,23 @@ __device__ __forceinline__ void flush(double* __restrict__ tile, const Acc& acc,
                                       int jx, int wx, int wy, int wz)
 {
   // rho and Jx: point (z = wz+a, y = wy+b, x = jx+wx+k)
-  double* p = tile + (wz + a) * SZ + (wy + b) * SY + (jx + wx) * 4;
+  double* p = tile + (wz + a) * SZR + (wy + b) * SYT + (jx + wx);
 #pragma unroll
   for (int k = 0; k < 4; k++)
-    p[k * 4 + 0] += acc.rho[k];
+    p[T_RHO + k] += acc.rho[k];
 #pragma unroll
   for (int k = 0; k < 3; k++)
-    p[(k + 1) * 4 + 1] += acc.jx[k];
+    p[T_JX + k + 1] += acc.jx[k];
   // Jy: point (z = wz+a, y = wy+k+1, x = jx+wx+b)
-  double* py = tile + (wz + a) * SZ + wy * SY + (jx + wx + b) * 4 + 2;
+  double* py = tile + T_JY + (wz + a) * SZT + wy * SYT + (jx + wx + b);
 #pragma unroll
   for (int k = 0; k < 3; k++)
-    py[(k + 1) * SY] += acc.jy[k];
+    py[(k + 1) * SYT] += acc.jy[k];
   // Jz: point (z = wz+k+1, y = wy+a, x = jx+wx+b)
-  double* pz = tile + wz * SZ + (wy + a) * SY + (jx + wx + b) * 4 + 3;
+  double* pz = tile + T_JZ + wz * SZT + (wy + a) * SYT + (jx + wx + b);
 #pragma unroll
   for (int k = 0; k < 3; k++)
-    pz[(k + 1) * SZ] += acc.jz[k];
+    pz[(k + 1) * SZT] += acc.jz[k];
 }
 
 } // namespace rowdep

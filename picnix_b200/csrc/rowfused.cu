@@ -80,7 +80,7 @@ __device__ __forceinline__ double interp27(const double* __restrict__ p, const d
       double rx = 0;
 #pragma unroll
       for (int jx = 0; jx < 3; jx++)
-        rx += p[(jz * FY + jy) * FROW + jx * 6] * wx[jx];
+        rx += p[jz * FSLAB + jy * FROW + jx * 6] * wx[jx];
       ry += rx * wy[jy];
     }
     rz += ry * wz[jz];
@@ -136,7 +136,7 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
       const int ty  = row - tz * FY;
       const double2 v = __ldg(reinterpret_cast<const double2*>(
                                   uf + ((int64_t)((gz + tz) * My + (gy + ty)) * Mx + gx) * 6) + col);
-      reinterpret_cast<double2*>(ftile + row * FROW)[col] = v;
+      reinterpret_cast<double2*>(ftile + tz * FSLAB + ty * FROW)[col] = v;
     }
   }
   for (int i = lane; i < TILE; i += 32)
@@ -235,12 +235,12 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
           const int tzi = 0, tzh = hz;
           // Yee staggering, pic/engine/velocity.hpp:442-447
           const double* F = ftile;
-          double ex = interp27(F + ((tzi * FY + tyi) * FX + txh) * 6 + 0, wiz, wiy, whx) * qmdt;
-          double ey = interp27(F + ((tzi * FY + tyh) * FX + txi) * 6 + 1, wiz, why, wix) * qmdt;
-          double ez = interp27(F + ((tzh * FY + tyi) * FX + txi) * 6 + 2, whz, wiy, wix) * qmdt;
-          double bx = interp27(F + ((tzh * FY + tyh) * FX + txi) * 6 + 3, whz, why, wix) * qmdt;
-          double by = interp27(F + ((tzh * FY + tyi) * FX + txh) * 6 + 4, whz, wiy, whx) * qmdt;
-          double bz = interp27(F + ((tzi * FY + tyh) * FX + txh) * 6 + 5, wiz, why, whx) * qmdt;
+          double ex = interp27(F + tzi * FSLAB + (tyi * FX + txh) * 6 + 0, wiz, wiy, whx) * qmdt;
+          double ey = interp27(F + tzi * FSLAB + (tyh * FX + txi) * 6 + 1, wiz, why, wix) * qmdt;
+          double ez = interp27(F + tzh * FSLAB + (tyi * FX + txi) * 6 + 2, whz, wiy, wix) * qmdt;
+          double bx = interp27(F + tzh * FSLAB + (tyh * FX + txi) * 6 + 3, whz, why, wix) * qmdt;
+          double by = interp27(F + tzh * FSLAB + (tyi * FX + txh) * 6 + 4, whz, wiy, whx) * qmdt;
+          double bz = interp27(F + tzi * FSLAB + (tyh * FX + txh) * 6 + 5, wiz, why, whx) * qmdt;
 
           push_momentum<Pusher>(ux, uy, uz, ex, ey, ez, bx, by, bz, rc.cc);
           x1 = x0;
@@ -278,6 +278,8 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
           key     = (z1 < zmin || z1 >= lim[1]) ? g.Ng : key;
           d.gindex[i] = key;
           atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, 1);
+          if (key == g.Ng)
+            note_leaver(d, seg, i);
         }
 
         double s1x[3], s1y[3], s1z[3];
@@ -369,14 +371,17 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
 
   // warp tile -> global current: one fp64 reduction per non-zero tile value
   const int gz0 = jz + g.Lb[0] - 2, gy0 = jy + g.Lb[1] - 2, gx0 = jx0 + g.Lb[2] - 2;
-  for (int idx = lane; idx < 25 * XS * 4; idx += 32) {
-    const int    tz = idx / (5 * XS * 4);
-    const int    r2 = idx - tz * (5 * XS * 4);
-    const int    ty = r2 / (XS * 4);
-    const int    e  = r2 - ty * (XS * 4);
-    const double v  = ws->tile[tz * SZ + ty * SY + e];
-    if (v != 0.0) {
-      atomicAdd(uj + ((int64_t)((gz0 + tz) * My + (gy0 + ty)) * Mx + gx0) * 4 + e, v);
+#pragma unroll
+  for (int comp = 0; comp < 4; comp++) {
+    const double* tc = ws->tile + tile_base(comp);
+    for (int idx = lane; idx < 25 * XS; idx += 32) {
+      const int    tz = idx / (5 * XS);
+      const int    r2 = idx - tz * (5 * XS);
+      const int    ty = r2 / XS;
+      const int    tx = r2 - ty * XS;
+      const double v  = tc[tz * tile_sz(comp) + ty * SYT + tx];
+      if (v != 0.0)
+        atomicAdd(uj + ((int64_t)((gz0 + tz) * My + (gy0 + ty)) * Mx + gx0 + tx) * 4 + comp, v);
     }
   }
 }

@@ -156,7 +156,8 @@ int launch_sort(picnix_arena* a, int c0, int cn)
 
   // XtensorParticle::swap (nix/xtensor_particle.hpp:120-123)
   std::swap(a->d.xu, a->d.xv);
-  a->pindex_valid = true;
+  a->pindex_valid     = true;
+  a->leave_list_valid = false; // slots changed
   return PICNIX_OK;
 }
 
