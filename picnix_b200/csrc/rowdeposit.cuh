@@ -240,6 +240,46 @@ __device__ __forceinline__ void flush(double* __restrict__ tile, const Acc& acc,
     pz[(k + 1) * SZT] += acc.jz[k];
 }
 
+// one staged particle straight into the warp tile (no register accumulators): used for the few
+// particles whose window differs from the run being accumulated, where accumulate() into a
+// temporary followed by flush() would move every value twice
+__device__ __forceinline__ void deposit_direct(double* __restrict__ tile, const double* __restrict__ rec,
+                                               int a, int b, int jx, int wx, int wy, int wz)
+{
+  const double2* r2 = reinterpret_cast<const double2*>(rec);
+  const double2  qa = r2[O_QS1X / 2 + 0], qb = r2[O_QS1X / 2 + 1];
+  const double2  p0 = r2[O_P / 2 + 0], p1 = r2[O_P / 2 + 1], p2 = r2[O_P / 2 + 2],
+                p3 = r2[O_P / 2 + 3], p4 = r2[O_P / 2 + 4];
+  const double2 a1 = r2[O_A1 / 2 + a];
+  const double2 a2 = r2[O_A2 / 2 + a];
+  const double2 ca = r2[O_C / 2 + a];
+  const double2 b1 = r2[O_B1 / 2 + b];
+  const double2 b2 = r2[O_B2 / 2 + b];
+  const double2 cb = r2[O_C / 2 + b];
+
+  const double c   = a1.x * b1.x;
+  const double wyz = b1.y * a1.y + b2.x * a2.x;
+  const double wzx = b2.y * a1.y + cb.y * a2.x;
+  const double wxy = b2.y * a2.y + cb.y * ca.x;
+
+  double* p = tile + (wz + a) * SZR + (wy + b) * SYT + (jx + wx);
+  p[T_RHO + 0] += c * qa.x;
+  p[T_RHO + 1] += c * qa.y;
+  p[T_RHO + 2] += c * qb.x;
+  p[T_RHO + 3] += c * qb.y;
+  p[T_JX + 1] += wyz * p0.x;
+  p[T_JX + 2] += wyz * p0.y;
+  p[T_JX + 3] += wyz * p1.x;
+  double* py = tile + T_JY + (wz + a) * SZT + wy * SYT + (jx + wx + b);
+  py[1 * SYT] += wzx * p1.y;
+  py[2 * SYT] += wzx * p2.x;
+  py[3 * SYT] += wzx * p2.y;
+  double* pz = tile + T_JZ + wz * SZT + (wy + a) * SYT + (jx + wx + b);
+  pz[1 * SZT] += wxy * p3.x;
+  pz[2 * SZT] += wxy * p3.y;
+  pz[3 * SZT] += wxy * p4.x;
+}
+
 } // namespace rowdep
 } // namespace picnix
 

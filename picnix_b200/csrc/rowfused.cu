@@ -312,10 +312,13 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
 
       // ---------------- phase 2: one staged particle per half-warp ----------------
       const int npass = (n + 1) >> 1;
+      int       pinf_next = ws->info[half];
       for (int k = 0; k < npass; k++) {
         const int     j    = 2 * k + half;
-        const int     pinf = ws->info[j];
+        const int     pinf = pinf_next;
         const double* rec  = ws->stg + j * REC;
+        // the info word of the next pass is requested now, so the vote below never waits for it
+        pinf_next = ws->info[(j + 2) & 31];
 
         // common case: both particles belong to the cells already being accumulated
         if (__all_sync(FULL, pinf == curinfo)) {
@@ -345,14 +348,10 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
           accumulate(acc, rec, a, b);
         }
         if (__any_sync(FULL, minor)) {
-          Acc tmp;
-          tmp.clear();
-          if (minor)
-            accumulate(tmp, rec, a, b);
 #pragma unroll
           for (int hh = 0; hh < 2; hh++) {
             if (half == hh && minor)
-              flush(ws->tile, tmp, a, b, jx, wx, wy, wz);
+              deposit_direct(ws->tile, rec, a, b, jx, wx, wy, wz);
             __syncwarp();
           }
         }
