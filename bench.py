@@ -66,6 +66,21 @@ def parse_args():
     return ap.parse_args()
 
 
+def ncu_traffic(np_local, ncell_local):
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/row_kernel_traffic.json); None when the capture was taken on another workload size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "row_kernel_traffic.json")) as fp:
+            t = json.load(fp)
+        if t["particles_per_launch"] != np_local or t["cells_per_launch"] != ncell_local:
+            return None, None
+        pipes = {k: t[k] for k in ("lsu_data_pipe_pct_of_peak", "fp64_pipe_pct_of_peak", "issue_active_pct",
+                                   "dram_throughput_pct_of_peak", "warps_per_sm") if k in t}
+        return t["dram_bytes_read"] + t["dram_bytes_write"], pipes
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -272,9 +287,12 @@ def b200_main(args, rank, world):
     alg_bytes = np_local * BYTES_PUSH_PER_PARTICLE + ncell_local * BYTES_PUSH_PER_CELL
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     step_bytes = np_local * BYTES_STEP_PER_PARTICLE + ncell_local * BYTES_STEP_PER_CELL
+    traffic, pipes = ncu_traffic(np_local, ncell_local)
     roofline = {
         "bound": "hbm", "kernel": "push_deposit_fused", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "limiter": "shared-memory data pipe (LSU wavefronts) and FP64 issue, not HBM: see ncu_pipes and DESIGN.md 3.1",
+        "ncu_pipes": pipes,
         "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * args.steps / elapsed_ms,
         "algorithmic_bytes_per_launch": alg_bytes,
         "whole_step": {"achieved": step_bytes * args.steps / (elapsed_ms * 1e-3) / 1e9 * (1 if world == 1 else 1),
