@@ -158,6 +158,10 @@ int picnix_cuda_push_position(picnix_arena_t* arena, int32_t chunk_begin, int32_
                               double delt);
 int picnix_cuda_deposit_current(picnix_arena_t* arena, int32_t chunk_begin, int32_t chunk_count,
                                 double delt);
+/* PicChunk::deposit_moment (pic/pic_chunk.cpp:525-534, pic/engine/moment.hpp): um <- 0, then the 14
+ * velocity moments of every species on the (order+1)^dim momentum-conserving stencil.  All local
+ * chunks; follow with boundary_begin/end(PICNIX_BOUNDARY_MOM) like PicApplication's diagnostics do. */
+int picnix_cuda_deposit_moment(picnix_arena_t* arena);
 /* PicChunk::sort_particle: count(reset) + counting sort, drops out-of-chunk particles */
 int picnix_cuda_sort_particle(picnix_arena_t* arena, int32_t chunk_begin, int32_t chunk_count);
 
@@ -196,6 +200,10 @@ int picnix_cuda_step(picnix_arena_t* arena, double delt, int32_t nstep);
 /* ---- diagnostics (PicChunk::get_diverror/get_energy, pic/pic_chunk.cpp:407-445) -------------- */
 int picnix_cuda_get_diverror(picnix_arena_t* arena, double* efd, double* bfd /* [nchunk] each */);
 int picnix_cuda_get_field_energy(picnix_arena_t* arena, double* efd, double* bfd);
+/* particle part of PicChunk::get_energy (pic/pic_chunk.cpp:428-438): per chunk and species the sum
+ * over interior cells of um[..][4]*c - um[..][0]*c^2 (rest mass subtracted); particle[nchunk*Ns].
+ * Needs deposit_moment + the BoundaryMom exchange first, as in the reference. */
+int picnix_cuda_get_particle_energy(picnix_arena_t* arena, double* particle);
 /* counters since arena creation: kernels launched by this library, particles pushed */
 int picnix_cuda_get_counters(const picnix_arena_t* arena, int64_t* kernel_launches,
                              int64_t* particle_pushes);

@@ -81,6 +81,8 @@ SIGNATURES = {
     "picnix_cuda_push_position": (_i32, [_vp, _i32, _i32, _dbl]),
     "picnix_cuda_deposit_current": (_i32, [_vp, _i32, _i32, _dbl]),
     "picnix_cuda_sort_particle": (_i32, [_vp, _i32, _i32]),
+    "picnix_cuda_deposit_moment": (_i32, [_vp]),
+    "picnix_cuda_get_particle_energy": (_i32, [_vp, _pd]),
     "picnix_cuda_push_deposit_fused": (_i32, [_vp, _i32, _i32, _dbl]),
     "picnix_cuda_boundary_begin": (_i32, [_vp, _i32]),
     "picnix_cuda_boundary_end": (_i32, [_vp, _i32]),

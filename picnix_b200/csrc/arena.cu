@@ -145,6 +145,14 @@ static int field_info(picnix_arena* a, int ichunk, int which, double** dptr, int
     *dptr  = a->d.ff + (int64_t)ichunk * ncell * 9;
     *elems = ncell * 18; // host layout
     return PICNIX_OK;
+  case PICNIX_FIELD_UM: {
+    int status = ensure_moment_array(a);
+    if (status != PICNIX_OK)
+      return status;
+    *dptr  = a->d.um + (int64_t)ichunk * ncell * a->g.Ns * 14;
+    *elems = ncell * a->g.Ns * 14;
+    return PICNIX_OK;
+  }
   default:
     return fail(a, PICNIX_ERR_INVALID, "unsupported field selector");
   }
@@ -426,6 +434,7 @@ int picnix_cuda_arena_destroy(picnix_arena_t* a)
   dev_free(a->d.uf);
   dev_free(a->d.uj);
   dev_free(a->d.ff);
+  dev_free(a->d.um);
   dev_free(a->d.clim);
   dev_free(a->d.nbr);
   dev_free(a->d.xu);
@@ -458,7 +467,7 @@ int picnix_cuda_arena_destroy(picnix_arena_t* a)
   for (auto& p : a->peers) {
     dev_free(p.d_send_desc);
     dev_free(p.d_recv_desc);
-    for (int m = 0; m < 2; m++) {
+    for (int m = 0; m < 3; m++) {
       dev_free(p.d_send_off[m]);
       dev_free(p.d_recv_off[m]);
       dev_free(p.d_send[m]);

@@ -55,6 +55,7 @@ struct DevPtrs {
   double*  uf;       // [nchunk][Mz][My][Mx][6]
   double*  uj;       // [nchunk][Mz][My][Mx][4]
   double*  ff;       // [nchunk][Mz][My][Mx][3][3]  (time level, E component)
+  double*  um;       // [nchunk][Mz][My][Mx][Ns][14] velocity moments; allocated by the first deposit_moment
   double*  clim;     // [nchunk][3][2] chunk limits  [z|y|x][min|max] (actual, not +-DBL_MAX)
   int*     nbr;      // [nchunk][27] neighbour codes
   double*  xu;       // [7][pcap]  SoA particle buffer "xu"
@@ -87,13 +88,13 @@ struct PeerPlan {
   std::vector<int>     recv_chunk, recv_dir; // what we receive (same canonical order on the peer)
   int*                 d_send_desc = nullptr; // device copy [nmsg][2]
   int*                 d_recv_desc = nullptr;
-  int64_t              send_elems[2] = {0, 0}; // doubles per mode (Emf, Cur)
-  int64_t              recv_elems[2] = {0, 0};
-  std::vector<int64_t> send_msg_off[2], recv_msg_off[2]; // element offset of each message
-  int64_t*             d_send_off[2] = {nullptr, nullptr};
-  int64_t*             d_recv_off[2] = {nullptr, nullptr};
-  double*              d_send[2] = {nullptr, nullptr};
-  double*              d_recv[2] = {nullptr, nullptr};
+  int64_t              send_elems[3] = {0, 0, 0}; // doubles per mode (Emf, Cur, Mom)
+  int64_t              recv_elems[3] = {0, 0, 0};
+  std::vector<int64_t> send_msg_off[3], recv_msg_off[3]; // element offset of each message
+  int64_t*             d_send_off[3] = {nullptr, nullptr, nullptr};
+  int64_t*             d_recv_off[3] = {nullptr, nullptr, nullptr};
+  double*              d_send[3] = {nullptr, nullptr, nullptr}; // Mom buffers are allocated on first use
+  double*              d_recv[3] = {nullptr, nullptr, nullptr};
   // particle mode: fixed-capacity staging, records of 8 doubles (7 comps + destination code)
   double*              d_psend = nullptr;
   double*              d_precv = nullptr;
@@ -145,6 +146,7 @@ struct picnix_arena {
   bool                   pindex_valid = false;  // pindex matches the particle order (after a sort)
   bool                   leave_list_valid = false; // DevPtrs::leave_idx describes the current keys
   bool                   force_generic = false; // testing: bypass the tiled kernels
+  bool                   deposit_mma   = false; // row kernel variant: deposit through the FP64 MMA unit
   int64_t                kernel_launches = 0;
   int64_t                particle_pushes = 0;
   int64_t                np_total_hint   = 0; // sum of np at last host-visible count
@@ -191,6 +193,11 @@ int launch_deposit_current(picnix_arena* a, int c0, int cn, double delt);
 int launch_push_deposit_fused(picnix_arena* a, int c0, int cn, double delt);
 int launch_deposit_rows(picnix_arena* a, int c0, int cn, double delt);
 bool row_kernel_applies(const picnix_arena* a);
+
+int ensure_moment_array(picnix_arena* a);
+int launch_deposit_moment(picnix_arena* a);
+int launch_moment_halo_local(picnix_arena* a);
+int launch_particle_energy(picnix_arena* a, double* particle);
 
 int launch_count(picnix_arena* a, int c0, int cn);
 int launch_sort(picnix_arena* a, int c0, int cn);

@@ -31,6 +31,10 @@ int picnix_cuda_set_option(picnix_arena_t* a, const char* key, int64_t value)
     a->force_generic = value != 0;
     return PICNIX_OK;
   }
+  if (std::string(key) == "deposit_mma") {
+    a->deposit_mma = value != 0;
+    return PICNIX_OK;
+  }
   return fail(a, PICNIX_ERR_INVALID, std::string("unknown option: ") + key);
 }
 
@@ -68,6 +72,20 @@ int picnix_cuda_deposit_current(picnix_arena_t* a, int32_t c0, int32_t cn, doubl
 {
   PICNIX_CHECK_RANGE(a, c0, cn);
   return launch_deposit_current(a, c0, cn, delt);
+}
+
+int picnix_cuda_deposit_moment(picnix_arena_t* a)
+{
+  if (a == nullptr)
+    return PICNIX_ERR_INVALID;
+  return launch_deposit_moment(a);
+}
+
+int picnix_cuda_get_particle_energy(picnix_arena_t* a, double* particle)
+{
+  if (a == nullptr || particle == nullptr)
+    return PICNIX_ERR_INVALID;
+  return launch_particle_energy(a, particle);
 }
 
 int picnix_cuda_sort_particle(picnix_arena_t* a, int32_t c0, int32_t cn)

@@ -182,8 +182,9 @@ __global__ void __launch_bounds__(HALO_THREADS) current_halo_local_kernel(Geom g
 template <int NCOMP, bool IS_CURRENT, bool IS_PACK>
 __global__ void __launch_bounds__(HALO_THREADS)
 remote_halo_kernel(Geom g, double* __restrict__ field, const int* __restrict__ desc,
-                   const int64_t* __restrict__ msg_off, double* __restrict__ buf)
+                   const int64_t* __restrict__ msg_off, double* __restrict__ buf, int ncomp_rt)
 {
+  const int ncomp = NCOMP > 0 ? NCOMP : ncomp_rt; // NCOMP == 0: moments, Ns * 14 components
   const int m     = blockIdx.x;
   const int chunk = desc[2 * m + 0];
   const int dir   = desc[2 * m + 1];
@@ -197,23 +198,23 @@ remote_halo_kernel(Geom g, double* __restrict__ field, const int* __restrict__ d
     bool interior = (IS_PACK != IS_CURRENT);
     lo[a]         = interior ? margin_lo(g, a, dc[a]) : ghost_lo(g, a, dc[a]);
   }
-  const int n   = len[0] * len[1] * len[2] * NCOMP;
+  const int n   = len[0] * len[1] * len[2] * ncomp;
   double*   msg = buf + msg_off[m];
 
   for (int e = threadIdx.x; e < n; e += blockDim.x) {
-    int k    = e % NCOMP;
-    int cell = e / NCOMP;
+    int k    = e % ncomp;
+    int cell = e / ncomp;
     int jx   = cell % len[2];
     int jy   = (cell / len[2]) % len[1];
     int jz   = cell / (len[2] * len[1]);
     int64_t c =
         (((int64_t)chunk * g.M[0] + lo[0] + jz) * g.M[1] + lo[1] + jy) * g.M[2] + lo[2] + jx;
     if (IS_PACK) {
-      msg[e] = field[c * NCOMP + k];
+      msg[e] = field[c * ncomp + k];
     } else if (IS_CURRENT) {
-      field[c * NCOMP + k] += msg[e];
+      field[c * ncomp + k] += msg[e];
     } else {
-      field[c * NCOMP + k] = msg[e];
+      field[c * ncomp + k] = msg[e];
     }
   }
 }
@@ -414,8 +415,8 @@ int build_comm_plan(picnix_arena* a)
 
     PeerPlan p;
     p.rank = r;
-    for (int mode = 0; mode < 2; mode++) {
-      int     ncomp = mode == 0 ? 6 : 4;
+    for (int mode = 0; mode < 3; mode++) {
+      int     ncomp = mode == 0 ? 6 : (mode == 1 ? 4 : g.Ns * 14);
       int64_t off   = 0;
       for (auto& m : send_by_rank[r]) {
         p.send_msg_off[mode].push_back(off);
@@ -464,11 +465,13 @@ int build_comm_plan(picnix_arena* a)
       return status;
     if ((status = upload_vector(a, &p.d_recv_desc, rdesc)) != PICNIX_OK)
       return status;
-    for (int mode = 0; mode < 2; mode++) {
+    for (int mode = 0; mode < 3; mode++) {
       if ((status = upload_vector(a, &p.d_send_off[mode], p.send_msg_off[mode])) != PICNIX_OK)
         return status;
       if ((status = upload_vector(a, &p.d_recv_off[mode], p.recv_msg_off[mode])) != PICNIX_OK)
         return status;
+      if (mode == PICNIX_BOUNDARY_MOM)
+        continue; // diagnostics cadence: buffers are allocated by the first moment exchange
       PICNIX_CUDA(a, cudaMalloc((void**)&p.d_send[mode],
                                 std::max<int64_t>(p.send_elems[mode], 1) * sizeof(double)));
       PICNIX_CUDA(a, cudaMalloc((void**)&p.d_recv[mode],
@@ -536,7 +539,7 @@ int launch_halo_begin(picnix_arena* a, int mode)
       int nmsg = (int)p.send_chunk.size();
       if (nmsg > 0) {
         remote_halo_kernel<6, false, true><<<nmsg, HALO_THREADS, 0, a->stream>>>(
-            g, a->d.uf, p.d_send_desc, p.d_send_off[0], p.d_send[0]);
+            g, a->d.uf, p.d_send_desc, p.d_send_off[0], p.d_send[0], 0);
         a->kernel_launches++;
       }
     }
@@ -550,12 +553,35 @@ int launch_halo_begin(picnix_arena* a, int mode)
       int nmsg = (int)p.send_chunk.size();
       if (nmsg > 0) {
         remote_halo_kernel<4, true, true><<<nmsg, HALO_THREADS, 0, a->stream>>>(
-            g, a->d.uj, p.d_send_desc, p.d_send_off[1], p.d_send[1]);
+            g, a->d.uj, p.d_send_desc, p.d_send_off[1], p.d_send[1], 0);
         a->kernel_launches++;
       }
     }
     current_halo_local_kernel<<<blocks, HALO_THREADS, 0, a->stream>>>(g, a->d);
     a->kernel_launches++;
+    break;
+  }
+  case PICNIX_BOUNDARY_MOM: {
+    // XtensorHaloMoment3D (nix/xtensor_halo3d.hpp:134-185): ghost -> neighbour, added into the
+    // interior margin, like the current but with Ns * 14 components per cell
+    int status = ensure_moment_array(a);
+    if (status != PICNIX_OK)
+      return status;
+    for (auto& p : a->peers) {
+      if (p.d_send[2] == nullptr) {
+        PICNIX_CUDA(a, cudaMalloc((void**)&p.d_send[2], std::max<int64_t>(p.send_elems[2], 1) * sizeof(double)));
+        PICNIX_CUDA(a, cudaMalloc((void**)&p.d_recv[2], std::max<int64_t>(p.recv_elems[2], 1) * sizeof(double)));
+      }
+      int nmsg = (int)p.send_chunk.size();
+      if (nmsg > 0) {
+        remote_halo_kernel<0, true, true><<<nmsg, HALO_THREADS, 0, a->stream>>>(
+            g, a->d.um, p.d_send_desc, p.d_send_off[2], p.d_send[2], g.Ns * 14);
+        a->kernel_launches++;
+      }
+    }
+    status = launch_moment_halo_local(a);
+    if (status != PICNIX_OK)
+      return status;
     break;
   }
   case PICNIX_BOUNDARY_PARTICLE: {
@@ -612,7 +638,7 @@ int launch_halo_end(picnix_arena* a, int mode)
       int nmsg = (int)p.recv_chunk.size();
       if (nmsg > 0) {
         remote_halo_kernel<6, false, false><<<nmsg, HALO_THREADS, 0, a->stream>>>(
-            g, a->d.uf, p.d_recv_desc, p.d_recv_off[0], p.d_recv[0]);
+            g, a->d.uf, p.d_recv_desc, p.d_recv_off[0], p.d_recv[0], 0);
         a->kernel_launches++;
       }
     }
@@ -622,7 +648,17 @@ int launch_halo_end(picnix_arena* a, int mode)
       int nmsg = (int)p.recv_chunk.size();
       if (nmsg > 0) {
         remote_halo_kernel<4, true, false><<<nmsg, HALO_THREADS, 0, a->stream>>>(
-            g, a->d.uj, p.d_recv_desc, p.d_recv_off[1], p.d_recv[1]);
+            g, a->d.uj, p.d_recv_desc, p.d_recv_off[1], p.d_recv[1], 0);
+        a->kernel_launches++;
+      }
+    }
+    break;
+  case PICNIX_BOUNDARY_MOM:
+    for (auto& p : a->peers) {
+      int nmsg = (int)p.recv_chunk.size();
+      if (nmsg > 0 && p.d_recv[2] != nullptr) {
+        remote_halo_kernel<0, true, false><<<nmsg, HALO_THREADS, 0, a->stream>>>(
+            g, a->d.um, p.d_recv_desc, p.d_recv_off[2], p.d_recv[2], g.Ns * 14);
         a->kernel_launches++;
       }
     }
@@ -673,7 +709,7 @@ int picnix_cuda_get_comm_buffer(picnix_arena_t* a, int32_t mode, int32_t peer_in
   if (a == nullptr || peer_index < 0 || peer_index >= (int)a->peers.size())
     return PICNIX_ERR_INVALID;
   PeerPlan& p = a->peers[peer_index];
-  if (mode == PICNIX_BOUNDARY_EMF || mode == PICNIX_BOUNDARY_CUR) {
+  if (mode == PICNIX_BOUNDARY_EMF || mode == PICNIX_BOUNDARY_CUR || mode == PICNIX_BOUNDARY_MOM) {
     *send_ptr   = p.d_send[mode];
     *recv_ptr   = p.d_recv[mode];
     *send_bytes = p.send_elems[mode] * (int64_t)sizeof(double);

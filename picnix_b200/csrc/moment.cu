@@ -1,0 +1,366 @@
+// -*- C++ -*-
+// Velocity moments and particle energy: PicChunk::deposit_moment (pic/pic_chunk.cpp:525-534,
+// pic/engine/moment.hpp), the particle part of PicChunk::get_energy (pic/pic_chunk.cpp:428-438) and
+// the BoundaryMom halo for neighbours inside the arena (nix/xtensor_halo3d.hpp:134-185).
+//
+//   um[chunk][Mz][My][Mx][Ns][14]   component order pic/engine/moment.hpp:19-32
+//       0 t   1 x   2 y   3 z   4 tt   5 xx   6 yy   7 zz   8 tx   9 ty   10 tz   11 xy   12 yz   13 zx
+//   per particle and stencil point (momentum-conserving shape, (Order+1)^Dim points):
+//       ww = m * wx * wy * wz,  gamma = sqrt(1 + u^2/c^2)
+//       t += ww, (x,y,z) += ww u/gamma, (tx,ty,tz) += ww u, tt += ww gamma c, pairs += ww u_i u_j / gamma
+//
+// Diagnostics cadence, not the per-step hot path.  Two kernels:
+//   * moment_cell_kernel  -- cell-ordered particles, even orders with (Order+1)^Dim <= 32 (the
+//     BASELINE configurations): one warp per (segment, cell); lane = stencil point; the warp walks the
+//     cell's particles (uniform loads), every lane keeps its 14 sums in registers and the cell
+//     costs 14 reductions per stencil point instead of 14 per particle and point.
+//   * moment_generic_kernel -- anything else: thread per particle, fp64 reductions to global.
+// Results differ from the reference by summation order only (tests: 1e-12 of max |um|).
+#include "particle_common.cuh"
+
+#include <algorithm>
+
+namespace picnix
+{
+
+namespace
+{
+
+constexpr int MTHREADS = 128;
+constexpr int NMOM     = 14;
+
+__device__ __forceinline__ void moment_terms(double ww, double ux, double uy, double uz, double gm,
+                                             double cc, double* t)
+{
+  t[0]  = ww;
+  t[1]  = ww * ux / gm;
+  t[2]  = ww * uy / gm;
+  t[3]  = ww * uz / gm;
+  t[4]  = ww * gm * cc;
+  t[5]  = ww * ux * ux / gm;
+  t[6]  = ww * uy * uy / gm;
+  t[7]  = ww * uz * uz / gm;
+  t[8]  = ww * ux;
+  t[9]  = ww * uy;
+  t[10] = ww * uz;
+  t[11] = ww * ux * uy / gm;
+  t[12] = ww * uy * uz / gm;
+  t[13] = ww * uz * ux / gm;
+}
+
+// weights and first stencil index of one axis (BaseMoment::local{1,2,3}d, moment.hpp:219-395)
+template <int Order>
+__device__ __forceinline__ int moment_axis(double x, double xmin, double dx, int lb, double* w)
+{
+  const double rdx = 1 / dx;
+  const int    ix  = digitize(x, xmin + 0.5 * dx * (Order % 2), rdx);
+  shape_mc<Order>(x, xmin + 0.5 * dx + (double)ix * dx, rdx, w);
+  return ix + lb - Order / 2;
+}
+
+template <int Dim, int Order>
+__global__ void __launch_bounds__(MTHREADS)
+moment_generic_kernel(Geom g, DevPtrs d, int blocks_per_seg)
+{
+  const int seg = blockIdx.x / blocks_per_seg;
+  const int ip  = (blockIdx.x - seg * blocks_per_seg) * blockDim.x + threadIdx.x;
+  if (ip >= d.np[seg])
+    return;
+  const int     chunk = seg / g.Ns, is = seg - chunk * g.Ns;
+  const int64_t i   = d.seg_off[seg] + ip;
+  const double* lim = d.clim + chunk * 6;
+  const double  ms  = d.qm[2 * is + 1];
+  constexpr int N   = Order + 1;
+
+  const double ux = d.xu[3 * d.pcap + i], uy = d.xu[4 * d.pcap + i], uz = d.xu[5 * d.pcap + i];
+  const double rc = 1 / g.cc;
+  const double gm = sqrt(1 + (ux * ux + uy * uy + uz * uz) * rc * rc);
+
+  double wx[N], wy[N], wz[N];
+  int    ix0, iy0 = g.Lb[1], iz0 = g.Lb[0];
+  ix0 = moment_axis<Order>(d.xu[0 * d.pcap + i], lim[4], g.del[2], g.Lb[2], wx);
+  if (Dim >= 2)
+    iy0 = moment_axis<Order>(d.xu[1 * d.pcap + i], lim[2], g.del[1], g.Lb[1], wy);
+  if (Dim >= 3)
+    iz0 = moment_axis<Order>(d.xu[2 * d.pcap + i], lim[0], g.del[0], g.Lb[0], wz);
+
+  double* um = d.um + (int64_t)chunk * g.Ng * g.Ns * NMOM;
+  for (int jz = 0; jz < (Dim >= 3 ? N : 1); jz++)
+    for (int jy = 0; jy < (Dim >= 2 ? N : 1); jy++)
+      for (int jx = 0; jx < N; jx++) {
+        double ww = ms * wx[jx];
+        if (Dim >= 2)
+          ww = ww * wy[jy];
+        if (Dim >= 3)
+          ww = ww * wz[jz];
+        double t[NMOM];
+        moment_terms(ww, ux, uy, uz, gm, g.cc, t);
+        double* m = um + ((((int64_t)(iz0 + jz) * g.M[1] + iy0 + jy) * g.M[2] + ix0 + jx) * g.Ns + is) * NMOM;
+#pragma unroll
+        for (int k = 0; k < NMOM; k++)
+          atomicAdd(m + k, t[k]);
+      }
+}
+
+__device__ __forceinline__ double pick(const double* w, int j, int n)
+{
+  double r = w[0];
+#pragma unroll
+  for (int k = 1; k < 5; k++)
+    if (k < n && j == k)
+      r = w[k];
+  return r;
+}
+
+// one warp per (segment, sort key); lane = stencil point
+template <int Dim, int Order>
+__global__ void __launch_bounds__(MTHREADS)
+moment_cell_kernel(Geom g, DevPtrs d)
+{
+  constexpr int N    = Order + 1;
+  constexpr int NPTS = Dim == 3 ? N * N * N : (Dim == 2 ? N * N : N);
+  const int64_t w    = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int     lane = threadIdx.x & 31;
+  const int     seg  = (int)(w / g.Ng);
+  const int     key  = (int)(w - (int64_t)seg * g.Ng);
+  if (seg >= g.nchunk * g.Ns)
+    return;
+  const int* pix = d.pindex + (int64_t)seg * (g.Ng + 1);
+  const int  pb = pix[key], pe = pix[key + 1];
+  if (pe <= pb)
+    return;
+
+  const int     chunk = seg / g.Ns, is = seg - chunk * g.Ns;
+  const int64_t off = d.seg_off[seg];
+  const double* lim = d.clim + chunk * 6;
+  const double  ms  = d.qm[2 * is + 1];
+  const double  rc  = 1 / g.cc;
+
+  // cell of this key (XtensorParticle::flatindex, nix/xtensor_particle.hpp:231-238); even order:
+  // every particle of the cell has the same stencil origin
+  const int jz = key / g.fsz, jy = (key - jz * g.fsz) / g.fsy, jx = key - jz * g.fsz - jy * g.fsy;
+  const int px = lane % N, py = Dim >= 2 ? (lane / N) % N : 0, pz = Dim >= 3 ? lane / (N * N) : 0;
+
+  double acc[NMOM];
+#pragma unroll
+  for (int k = 0; k < NMOM; k++)
+    acc[k] = 0;
+
+  for (int ip = pb; ip < pe; ip++) {
+    const int64_t i  = off + ip;
+    const double  ux = d.xu[3 * d.pcap + i], uy = d.xu[4 * d.pcap + i], uz = d.xu[5 * d.pcap + i];
+    const double  gm = sqrt(1 + (ux * ux + uy * uy + uz * uz) * rc * rc);
+    double        wx[N], wy[N], wz[N];
+    moment_axis<Order>(d.xu[0 * d.pcap + i], lim[4], g.del[2], g.Lb[2], wx);
+    double ww = ms * pick(wx, px, N);
+    if (Dim >= 2) {
+      moment_axis<Order>(d.xu[1 * d.pcap + i], lim[2], g.del[1], g.Lb[1], wy);
+      ww = ww * pick(wy, py, N);
+    }
+    if (Dim >= 3) {
+      moment_axis<Order>(d.xu[2 * d.pcap + i], lim[0], g.del[0], g.Lb[0], wz);
+      ww = ww * pick(wz, pz, N);
+    }
+    double t[NMOM];
+    moment_terms(ww, ux, uy, uz, gm, g.cc, t);
+#pragma unroll
+    for (int k = 0; k < NMOM; k++)
+      acc[k] += t[k];
+  }
+
+  if (lane < NPTS) {
+    const int ix = jx + g.Lb[2] - Order / 2 + px;
+    const int iy = Dim >= 2 ? jy + g.Lb[1] - Order / 2 + py : g.Lb[1];
+    const int iz = Dim >= 3 ? jz + g.Lb[0] - Order / 2 + pz : g.Lb[0];
+    double*   m  = d.um + (int64_t)chunk * g.Ng * g.Ns * NMOM +
+                ((((int64_t)iz * g.M[1] + iy) * g.M[2] + ix) * g.Ns + is) * NMOM;
+#pragma unroll
+    for (int k = 0; k < NMOM; k++)
+      atomicAdd(m + k, acc[k]);
+  }
+}
+
+// BoundaryMom between chunks of the arena: interior-margin cells add the neighbours' ghost cells,
+// directions visited in the reference's unpack order (same structure as the current halo)
+__global__ void __launch_bounds__(256) moment_halo_local_kernel(Geom g, DevPtrs d)
+{
+  const int     ncomp = g.Ns * NMOM;
+  const int64_t e     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)g.nchunk * g.Ng * ncomp)
+    return;
+  const int64_t t     = e / ncomp;
+  const int     k     = (int)(e - t * ncomp);
+  const int     chunk = (int)(t / g.Ng);
+  int           r     = (int)(t - (int64_t)chunk * g.Ng);
+  int           idx[3];
+  idx[0] = r / (g.M[1] * g.M[2]);
+  r -= idx[0] * g.M[1] * g.M[2];
+  idx[1] = r / g.M[2];
+  idx[2] = r - idx[1] * g.M[2];
+
+  bool reach[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    if (idx[a] < g.Lb[a] || idx[a] > g.Ub[a])
+      return;
+    reach[a][0] = g.has_dim[a] && idx[a] < g.Lb[a] + g.nb;
+    reach[a][1] = true;
+    reach[a][2] = g.has_dim[a] && idx[a] > g.Ub[a] - g.nb;
+  }
+  double acc     = d.um[t * ncomp + k];
+  bool   touched = false;
+  for (int dz = 0; dz < 3; dz++) {
+    if (!reach[0][dz])
+      continue;
+    for (int dy = 0; dy < 3; dy++) {
+      if (!reach[1][dy])
+        continue;
+      for (int dx = 0; dx < 3; dx++) {
+        if (!reach[2][dx] || (dz == 1 && dy == 1 && dx == 1))
+          continue;
+        const int nb = d.nbr[chunk * NBSIZE + 9 * dz + 3 * dy + dx];
+        if (nb < 0)
+          continue;
+        const int     sz = idx[0] + (dz == 0 ? g.dims[0] : (dz == 2 ? -g.dims[0] : 0));
+        const int     sy = idx[1] + (dy == 0 ? g.dims[1] : (dy == 2 ? -g.dims[1] : 0));
+        const int     sx = idx[2] + (dx == 0 ? g.dims[2] : (dx == 2 ? -g.dims[2] : 0));
+        const int64_t s  = (((int64_t)nb * g.M[0] + sz) * g.M[1] + sy) * g.M[2] + sx;
+        acc += d.um[s * ncomp + k];
+        touched = true;
+      }
+    }
+  }
+  if (touched)
+    d.um[t * ncomp + k] = acc;
+}
+
+// particle[is] = sum over interior cells of um[..][is][4] * c - um[..][is][0] * c^2, per chunk
+__global__ void __launch_bounds__(256) particle_energy_kernel(Geom g, DevPtrs d, double* out)
+{
+  __shared__ double red[256];
+  const int chunk = blockIdx.x / g.Ns, is = blockIdx.x - chunk * g.Ns;
+  const int nz = g.Ub[0] - g.Lb[0] + 1, ny = g.Ub[1] - g.Lb[1] + 1, nx = g.Ub[2] - g.Lb[2] + 1;
+  double    sum = 0;
+  for (int c = threadIdx.x; c < nz * ny * nx; c += blockDim.x) {
+    const int     iz = c / (ny * nx) + g.Lb[0], iy = (c / nx) % ny + g.Lb[1], ix = c % nx + g.Lb[2];
+    const double* m  = d.um + ((((int64_t)chunk * g.M[0] + iz) * g.M[1] + iy) * g.M[2] + ix) * g.Ns * NMOM +
+                      (int64_t)is * NMOM;
+    sum += m[4] * g.cc - m[0] * g.cc * g.cc;
+  }
+  red[threadIdx.x] = sum;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s)
+      red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    out[blockIdx.x] = red[0];
+}
+
+template <int Dim, int Order>
+void launch_moment_kernels(picnix_arena* a)
+{
+  const Geom&   g    = a->g;
+  constexpr int N    = Order + 1;
+  constexpr int NPTS = Dim == 3 ? N * N * N : (Dim == 2 ? N * N : N);
+  if (a->pindex_valid && Order % 2 == 0 && NPTS <= 32 && !a->force_generic) {
+    const int64_t warps  = (int64_t)a->nseg * g.Ng;
+    const int64_t blocks = (warps * 32 + MTHREADS - 1) / MTHREADS;
+    moment_cell_kernel<Dim, Order><<<(unsigned)blocks, MTHREADS, 0, a->stream>>>(g, a->d);
+  } else {
+    int maxcap = 0;
+    for (int s = 0; s < a->nseg; s++)
+      maxcap = std::max(maxcap, a->seg_cap[s]);
+    const int bps = (maxcap + MTHREADS - 1) / MTHREADS;
+    if (bps > 0)
+      moment_generic_kernel<Dim, Order><<<bps * a->nseg, MTHREADS, 0, a->stream>>>(g, a->d, bps);
+  }
+  a->kernel_launches++;
+}
+
+template <int Dim>
+void launch_moment_order(picnix_arena* a)
+{
+  switch (a->g.order) {
+  case 1:
+    launch_moment_kernels<Dim, 1>(a);
+    break;
+  case 2:
+    launch_moment_kernels<Dim, 2>(a);
+    break;
+  case 3:
+    launch_moment_kernels<Dim, 3>(a);
+    break;
+  default:
+    launch_moment_kernels<Dim, 4>(a);
+    break;
+  }
+}
+
+} // namespace
+
+int ensure_moment_array(picnix_arena* a)
+{
+  if (a->d.um != nullptr)
+    return PICNIX_OK;
+  const size_t bytes = (size_t)a->g.nchunk * a->g.Ng * a->g.Ns * NMOM * sizeof(double);
+  PICNIX_CUDA(a, cudaMalloc((void**)&a->d.um, bytes));
+  PICNIX_CUDA(a, cudaMemsetAsync(a->d.um, 0, bytes, a->stream));
+  return PICNIX_OK;
+}
+
+int launch_deposit_moment(picnix_arena* a)
+{
+  if (!a->particles_allocated)
+    return fail(a, PICNIX_ERR_INVALID, "no particles allocated");
+  int status = ensure_moment_array(a);
+  if (status != PICNIX_OK)
+    return status;
+  const Geom& g = a->g;
+  // fill_all(um, 0), pic/engine/moment.hpp:104,166
+  PICNIX_CUDA(a, cudaMemsetAsync(a->d.um, 0, (size_t)g.nchunk * g.Ng * g.Ns * NMOM * sizeof(double),
+                                 a->stream));
+  switch (g.dimension) {
+  case 1:
+    launch_moment_order<1>(a);
+    break;
+  case 2:
+    launch_moment_order<2>(a);
+    break;
+  default:
+    launch_moment_order<3>(a);
+    break;
+  }
+  return check_cuda(a, cudaGetLastError(), "deposit_moment");
+}
+
+int launch_moment_halo_local(picnix_arena* a)
+{
+  int status = ensure_moment_array(a);
+  if (status != PICNIX_OK)
+    return status;
+  const int64_t n = (int64_t)a->g.nchunk * a->g.Ng * a->g.Ns * NMOM;
+  moment_halo_local_kernel<<<(unsigned)((n + 255) / 256), 256, 0, a->stream>>>(a->g, a->d);
+  a->kernel_launches++;
+  return check_cuda(a, cudaGetLastError(), "moment halo");
+}
+
+int launch_particle_energy(picnix_arena* a, double* particle)
+{
+  int status = ensure_moment_array(a);
+  if (status != PICNIX_OK)
+    return status;
+  const int n = a->g.nchunk * a->g.Ns;
+  double*   d_out = nullptr;
+  PICNIX_CUDA(a, cudaMalloc((void**)&d_out, n * sizeof(double)));
+  particle_energy_kernel<<<n, 256, 0, a->stream>>>(a->g, a->d, d_out);
+  a->kernel_launches++;
+  cudaError_t err = cudaMemcpyAsync(particle, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, a->stream);
+  if (err == cudaSuccess)
+    err = cudaStreamSynchronize(a->stream);
+  cudaFree(d_out);
+  return check_cuda(a, err, "particle energy");
+}
+
+} // namespace picnix

@@ -7,7 +7,7 @@
 //   FUSED = false: deposit only, old position from xv, new position from xu (PicChunk::deposit_current)
 // One block per (chunk, z, group of WARPS rows in y, x-segment of RX cells), one warp per row; the
 // particles of a row segment are contiguous in the cell-sorted arrays: [pindex[key0], pindex[key0+RX]).
-#include "rowdeposit.cuh"
+#include "rowmma.cuh"
 
 namespace picnix
 {
@@ -385,6 +385,299 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
   }
 }
 
+constexpr int MMA_BLOCKS_PER_SM = 3;
+
+// accumulators of a run (cell + window) -> global uj; info word as in rowdeposit.cuh
+template <int ROUND>
+__device__ __forceinline__ void flush_run(double* __restrict__ uj, int My, int Mx, const rowmma::Frag& acc,
+                                          int fg, int fk, int info, int oz0, int oy0, int ox0)
+{
+  const int jx = info & 0xff;
+  const int wx = (info >> 8) & 1, wy = (info >> 9) & 1, wz = (info >> 10) & 1;
+  rowmma::flush_global<ROUND>(uj, My, Mx, acc, fg, fk, oz0 + wz, oy0 + wy, ox0 + jx + wx);
+}
+
+// one staging round of a batch: the staged particles, four at a time, into the accumulators
+template <int ROUND>
+__device__ __forceinline__ void mma_round(rowmma::Frag& acc, int& curinfo, const rowmma::WarpSmem* ws,
+                                          int ngroup, int fg, int fk, double* __restrict__ uj, int My,
+                                          int Mx, int oz0, int oy0, int ox0)
+{
+  const unsigned FULL = 0xffffffffu;
+  for (int kg = 0; kg < ngroup; kg++) {
+    const int my = ws->info[kg * 4 + fk];
+    // common case: the four particles continue the run being accumulated
+    if (__all_sync(FULL, my == curinfo)) {
+      rowmma::mma_group(acc, ws->stg, kg, fg, fk, true);
+      continue;
+    }
+    bool pending = (my >> 11) & 1;
+    while (__any_sync(FULL, pending)) {
+      const unsigned m   = __ballot_sync(FULL, pending);
+      const int      cur = __shfl_sync(FULL, my, __ffs(m) - 1);
+      const bool     sel = pending && my == cur;
+      if (((cur >> 8) & 7) == 7) {
+        // majority window: a new run starts when the cell changes
+        if (cur != curinfo) {
+          if (curinfo != -1)
+            flush_run<ROUND>(uj, My, Mx, acc, fg, fk, curinfo, oz0, oy0, ox0);
+          acc.clear();
+          curinfo = cur;
+        }
+        rowmma::mma_group(acc, ws->stg, kg, fg, fk, sel);
+      } else {
+        // window shifted down in some axis (particle moved to the lower cell): on its own
+        rowmma::Frag tmp;
+        tmp.clear();
+        rowmma::mma_group(tmp, ws->stg, kg, fg, fk, sel);
+        flush_run<ROUND>(uj, My, Mx, tmp, fg, fk, cur, oz0, oy0, ox0);
+      }
+      pending = pending && !sel;
+    }
+  }
+}
+
+template <bool FUSED, int Pusher, int Interp>
+__global__ void __launch_bounds__(THREADS, MMA_BLOCKS_PER_SM)
+row_mma_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double*   ftile = reinterpret_cast<double*>(smem_raw);
+  rowmma::WarpSmem* wsm = reinterpret_cast<rowmma::WarpSmem*>(smem_raw + sizeof(double) * FTILE);
+
+  const int      lane = threadIdx.x & 31;
+  const int      warp = threadIdx.x >> 5;
+  const int      fg   = lane >> 2; // MMA fragment row / column group
+  const int      fk   = lane & 3;  // MMA contraction index (particle inside a group of 4)
+  const unsigned FULL = 0xffffffffu;
+  rowmma::WarpSmem* ws = wsm + warp;
+
+  // block -> (chunk, z, y group, x segment)
+  const int nsegx = g.dims[2] / RX;
+  const int nygrp = g.dims[1] / WARPS;
+  int       r     = blockIdx.x;
+  const int lc    = r / (g.dims[0] * nygrp * nsegx);
+  r -= lc * g.dims[0] * nygrp * nsegx;
+  const int jz = r / (nygrp * nsegx);
+  r -= jz * nygrp * nsegx;
+  const int jy0   = (r / nsegx) * WARPS;
+  const int jx0   = (r - (r / nsegx) * nsegx) * RX;
+  const int jy    = jy0 + warp;
+  const int chunk = c0 + lc;
+
+  const double* lim = d.clim + chunk * 6;
+  double*       uj  = d.uj + (int64_t)chunk * g.Ng * 4;
+  const int     My = g.M[1], Mx = g.M[2];
+
+  // ---- stage the field tile (global layout [z][y][x][6], 16-byte copies) ----
+  if (FUSED) {
+    const double* uf = d.uf + (int64_t)chunk * g.Ng * 6;
+    const int     gz = jz + g.Lb[0] - 1, gy = jy0 + g.Lb[1] - 1, gx = jx0 + g.Lb[2] - 1;
+    for (int e = threadIdx.x; e < FZ * FY * (FROW / 2); e += THREADS) {
+      const int row = e / (FROW / 2);
+      const int col = e - row * (FROW / 2);
+      const int tz  = row / FY;
+      const int ty  = row - tz * FY;
+      const double2 v = __ldg(reinterpret_cast<const double2*>(
+                                  uf + ((int64_t)((gz + tz) * My + (gy + ty)) * Mx + gx) * 6) + col);
+      reinterpret_cast<double2*>(ftile + tz * FSLAB + ty * FROW)[col] = v;
+    }
+  }
+  if (FUSED)
+    __syncthreads();
+  else
+    __syncwarp();
+
+  const double xmin = lim[4], ymin = lim[2], zmin = lim[0];
+  const double rdx = rc.rd[2], rdy = rc.rd[1], rdz = rc.rd[0];
+  const double dx = rc.del[2], dy = rc.del[1], dz = rc.del[0];
+  // cell-centre ("integer") and cell-edge ("half") grid points of this row, pic/engine/velocity.hpp:304-315
+  const double yig = ymin + 0.5 * dy + (double)jy * dy;
+  const double zig = zmin + 0.5 * dz + (double)jz * dz;
+  const double yh0 = ymin + (double)jy * dy, yh1 = ymin + (double)(jy + 1) * dy;
+  const double zh0 = zmin + (double)jz * dz, zh1 = zmin + (double)(jz + 1) * dz;
+  const double xigrid = xmin + 0.5 * dx, yigrid = ymin + 0.5 * dy, zigrid = zmin + 0.5 * dz;
+  const int    key0 = jz * g.fsz + jy * g.fsy + jx0;
+  // global index of stencil slot 0 (two cells left of / below the cell) of this row's first cell
+  const int    oz0 = jz + g.Lb[0] - 2, oy0 = jy + g.Lb[1] - 2, ox0 = jx0 + g.Lb[2] - 2;
+
+  for (int is = 0; is < g.Ns; is++) {
+    const int     seg = chunk * g.Ns + is;
+    const int64_t off = d.seg_off[seg];
+    const int*    pix = d.pindex + (int64_t)seg * (g.Ng + 1);
+    const int     pb = pix[key0], pe = pix[key0 + RX];
+    const double  q    = d.qm[2 * is];
+    const double  qmdt = 0.5 * q / d.qm[2 * is + 1] * delt;
+
+    rowmma::Frag acc0, acc1; // round 0: rho, Jx; round 1: Jy, Jz
+    acc0.clear();
+    acc1.clear();
+    int curinfo0 = -1, curinfo1 = -1; // info word of the cell each accumulator set belongs to
+
+    // the six phase-space components of the NEXT batch are requested before phase 2 of the current
+    // one, so their HBM latency is hidden behind the accumulation loop
+    double pfx = 0, pfy = 0, pfz = 0, pfux = 0, pfuy = 0, pfuz = 0;
+    if (FUSED && pb + lane < pe) {
+      const int64_t i = off + pb + lane;
+      pfx  = d.xu[0 * d.pcap + i];
+      pfy  = d.xu[1 * d.pcap + i];
+      pfz  = d.xu[2 * d.pcap + i];
+      pfux = d.xu[3 * d.pcap + i];
+      pfuy = d.xu[4 * d.pcap + i];
+      pfuz = d.xu[5 * d.pcap + i];
+    }
+
+    for (int base = pb; base < pe; base += 32) {
+      const int n = min(32, pe - base);
+
+      // ---------------- phase 1: one particle per lane ----------------
+      int             inf = 0;
+      rowmma::Factors fac;
+      if (lane < n) {
+        const int64_t i = off + base + lane;
+        double        x0, y0, z0, x1, y1, z1;
+        double        s0x[3], s0y[3], s0z[3];
+        int           cx; // old cell in x, relative to the chunk
+        if (FUSED) {
+          x0        = pfx;
+          y0        = pfy;
+          z0        = pfz;
+          double ux = pfux;
+          double uy = pfuy;
+          double uz = pfuz;
+
+          // weights on the centre grid (MC or WT) and on the edge grid (MC); the particle is in
+          // row (jz, jy) by construction of the sort, only its x cell has to be found
+          double wix[3], whx[3], wiy[3], why[3], wiz[3], whz[3];
+          cx = digitize(x0, xmin, rdx);
+          const double cxf = (double)cx;
+          const double dix = (x0 - (xigrid + cxf * dx)) * rdx;
+          const double diy = (y0 - yig) * rdy;
+          const double diz = (z0 - zig) * rdz;
+          shape2(dix, s0x);
+          shape2(diy, s0y);
+          shape2(diz, s0z);
+          if (Interp == PICNIX_INTERP_MC) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              wix[k] = s0x[k];
+              wiy[k] = s0y[k];
+              wiz[k] = s0z[k];
+            }
+          } else {
+            shape_wt<2>(x0, xigrid + cxf * dx, rdx, rc.cfl[2], 1 / rc.cfl[2], wix);
+            shape_wt<2>(y0, yig, rdy, rc.cfl[1], 1 / rc.cfl[1], wiy);
+            shape_wt<2>(z0, zig, rdz, rc.cfl[0], 1 / rc.cfl[0], wiz);
+          }
+          // nearest cell edge: the one to the right when the particle sits right of the centre
+          const int hx = dix >= 0.0, hy = diy >= 0.0, hz = diz >= 0.0;
+          shape2((x0 - (xmin + (cxf + (double)hx) * dx)) * rdx, whx);
+          shape2((y0 - (hy ? yh1 : yh0)) * rdy, why);
+          shape2((z0 - (hz ? zh1 : zh0)) * rdz, whz);
+
+          // first stencil point inside the tile for the centre (i) and edge (h) grids
+          const int txi = cx - jx0, txh = txi + hx;
+          const int tyi = warp, tyh = warp + hy;
+          const int tzi = 0, tzh = hz;
+          // Yee staggering, pic/engine/velocity.hpp:442-447
+          const double* F = ftile;
+          double ex = interp27(F + tzi * FSLAB + (tyi * FX + txh) * 6 + 0, wiz, wiy, whx) * qmdt;
+          double ey = interp27(F + tzi * FSLAB + (tyh * FX + txi) * 6 + 1, wiz, why, wix) * qmdt;
+          double ez = interp27(F + tzh * FSLAB + (tyi * FX + txi) * 6 + 2, whz, wiy, wix) * qmdt;
+          double bx = interp27(F + tzh * FSLAB + (tyh * FX + txi) * 6 + 3, whz, why, wix) * qmdt;
+          double by = interp27(F + tzh * FSLAB + (tyi * FX + txh) * 6 + 4, whz, wiy, whx) * qmdt;
+          double bz = interp27(F + tzi * FSLAB + (tyh * FX + txh) * 6 + 5, wiz, why, whx) * qmdt;
+
+          push_momentum<Pusher>(ux, uy, uz, ex, ey, ez, bx, by, bz, rc.cc);
+          x1 = x0;
+          y1 = y0;
+          z1 = z0;
+          push_position(x1, y1, z1, ux, uy, uz, rc.rc, delt);
+          d.xu[0 * d.pcap + i] = x1;
+          d.xu[1 * d.pcap + i] = y1;
+          d.xu[2 * d.pcap + i] = z1;
+          d.xu[3 * d.pcap + i] = ux;
+          d.xu[4 * d.pcap + i] = uy;
+          d.xu[5 * d.pcap + i] = uz;
+        } else {
+          x0 = d.xv[0 * d.pcap + i];
+          y0 = d.xv[1 * d.pcap + i];
+          z0 = d.xv[2 * d.pcap + i];
+          x1 = d.xu[0 * d.pcap + i];
+          y1 = d.xu[1 * d.pcap + i];
+          z1 = d.xu[2 * d.pcap + i];
+          cx = digitize(x0, xmin, rdx);
+          shape2((x0 - (xigrid + (double)cx * dx)) * rdx, s0x);
+          shape2((y0 - yig) * rdy, s0y);
+          shape2((z0 - zig) * rdz, s0z);
+        }
+
+        // new cell: XtensorParticle::count (nix/xtensor_particle.hpp:324-357) and the "after"
+        // weights of the Esirkepov scheme share the digitisation (even order: same cell origin)
+        const int ix1 = digitize(x1, xmin, rdx);
+        const int iy1 = digitize(y1, ymin, rdy);
+        const int iz1 = digitize(z1, zmin, rdz);
+        if (FUSED) {
+          int key = iz1 * g.fsz + iy1 * g.fsy + ix1;
+          key     = (x1 < xmin || x1 >= lim[5]) ? g.Ng : key;
+          key     = (y1 < ymin || y1 >= lim[3]) ? g.Ng : key;
+          key     = (z1 < zmin || z1 >= lim[1]) ? g.Ng : key;
+          d.gindex[i] = key;
+          atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, 1);
+          if (key == g.Ng)
+            note_leaver(d, seg, i);
+        }
+
+        double s1x[3], s1y[3], s1z[3];
+        shape2((x1 - (xigrid + (double)ix1 * dx)) * rdx, s1x);
+        shape2((y1 - (yigrid + (double)iy1 * dy)) * rdy, s1y);
+        shape2((z1 - (zigrid + (double)iz1 * dz)) * rdz, s1z);
+        const int shx = ix1 - cx, shy = iy1 - jy, shz = iz1 - jz;
+        const int jx  = cx - jx0;
+        if (abs(shx) <= 1 && abs(shy) <= 1 && abs(shz) <= 1 && jx >= 0 && jx < RX) {
+          const AxisFactors fx = window_factors(s0x, s1x, shx);
+          const AxisFactors fy = window_factors(s0y, s1y, shy);
+          const AxisFactors fz = window_factors(s0z, s1z, shz);
+          fac = rowmma::make_factors(fx, fy, fz, q, rc.ddt[2], rc.ddt[1], rc.ddt[0]);
+          inf = make_info(jx, fx.w, fy.w, fz.w);
+        } else {
+          defer_far_mover(d, chunk, q, x0, y0, z0, x1, y1, z1);
+        }
+      }
+      ws->info[lane] = inf;
+      if (FUSED && base + 32 + lane < pe) {
+        const int64_t i = off + base + 32 + lane;
+        pfx  = d.xu[0 * d.pcap + i];
+        pfy  = d.xu[1 * d.pcap + i];
+        pfz  = d.xu[2 * d.pcap + i];
+        pfux = d.xu[3 * d.pcap + i];
+        pfuy = d.xu[4 * d.pcap + i];
+        pfuz = d.xu[5 * d.pcap + i];
+      }
+      __syncwarp();
+
+      // ---------------- phase 2: groups of 4 staged particles through the FP64 MMA ----------------
+      const int ngroup = (n + 3) >> 2;
+      if (inf)
+        rowmma::stage_round<0>(ws->stg, lane, fac);
+      __syncwarp();
+      mma_round<0>(acc0, curinfo0, ws, ngroup, fg, fk, uj, My, Mx, oz0, oy0, ox0);
+      __syncwarp();
+      if (inf)
+        rowmma::stage_round<1>(ws->stg, lane, fac);
+      __syncwarp();
+      mma_round<1>(acc1, curinfo1, ws, ngroup, fg, fk, uj, My, Mx, oz0, oy0, ox0);
+      __syncwarp();
+    }
+
+    // end of this species' particles in the segment
+    if (curinfo0 != -1)
+      flush_run<0>(uj, My, Mx, acc0, fg, fk, curinfo0, oz0, oy0, ox0);
+    if (curinfo1 != -1)
+      flush_run<1>(uj, My, Mx, acc1, fg, fk, curinfo1, oz0, oy0, ox0);
+  }
+}
+
 template <bool FUSED>
 int launch_row_kernel(picnix_arena* a, int c0, int cn, double delt)
 {
@@ -405,7 +698,12 @@ int launch_row_kernel(picnix_arena* a, int c0, int cn, double delt)
   PICNIX_CUDA(a, cudaMemsetAsync(a->d.far_count, 0, sizeof(int), a->stream));
 
 #define PICNIX_ROW_LAUNCH(P, I)                                                                    \
-  {                                                                                                \
+  if (a->deposit_mma) {                                                                            \
+    auto kern = row_mma_kernel<FUSED, P, I>;                                                       \
+    PICNIX_CUDA(a, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                        (int)rowmma::SMEM_BYTES));                                 \
+    kern<<<blocks, THREADS, rowmma::SMEM_BYTES, a->stream>>>(g, a->d, rc, c0, cn, delt);           \
+  } else {                                                                                         \
     auto kern = row_kernel<FUSED, P, I>;                                                           \
     PICNIX_CUDA(a, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                         (int)SMEM_BYTES));                                         \

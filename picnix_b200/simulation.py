@@ -100,7 +100,7 @@ class CudaSim:
 
     # -- state -----------------------------------------------------------------------------
     def _field_shape(self, which):
-        tail = {capi.FIELD_UF: (6,), capi.FIELD_UJ: (4,), capi.FIELD_FF: (3, 6)}[which]
+        tail = {capi.FIELD_UF: (6,), capi.FIELD_UJ: (4,), capi.FIELD_FF: (3, 6), capi.FIELD_UM: (self.Ns, 14)}[which]
         return self.shape + tail
 
     def set_species(self, isp, q, m):
@@ -201,6 +201,18 @@ class CudaSim:
     def deposit_current(self, dt):
         self.commit()
         self._check(self.lib.picnix_cuda_deposit_current(self.h, 0, -1, dt))
+
+    def deposit_moment(self):
+        self.commit()
+        self._check(self.lib.picnix_cuda_deposit_moment(self.h))
+
+    def get_energy(self):
+        """PicChunk::get_energy per chunk: columns efd, bfd, particle[0..Ns-1] (after deposit_moment
+        and the BoundaryMom exchange, like the reference's history diagnostic)."""
+        fe = self.get_field_energy()
+        p = np.zeros(self.nchunk * self.Ns)
+        self._check(self.lib.picnix_cuda_get_particle_energy(self.h, p))
+        return np.concatenate([fe, p.reshape(self.nchunk, self.Ns)], axis=1)
 
     def push_deposit_fused(self, dt):
         self.commit()
