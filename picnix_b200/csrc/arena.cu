@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace picnix
@@ -367,6 +368,9 @@ int picnix_cuda_arena_create(const picnix_config_t* cfg, const int32_t* boundary
   }
 
   auto a = new picnix_arena();
+  // tuning/testing override of the row-kernel variant (same as set_option("deposit_mma"))
+  if (const char* env = std::getenv("PICNIX_DEPOSIT_MMA"))
+    a->deposit_mma = std::atoi(env) != 0;
   a->cfg = *cfg;
   std::memset(&a->g, 0, sizeof(a->g));
   std::memset(&a->d, 0, sizeof(a->d));

@@ -697,9 +697,11 @@ int launch_row_kernel(picnix_arena* a, int c0, int cn, double delt)
   rc.delt = delt;
   PICNIX_CUDA(a, cudaMemsetAsync(a->d.far_count, 0, sizeof(int), a->stream));
 
+  // the FP64-MMA deposit is an experiment kept for the record (slower, see rowmma.cuh); it is only
+  // instantiated for the benchmark configuration (fused, Boris, MC)
 #define PICNIX_ROW_LAUNCH(P, I)                                                                    \
-  if (a->deposit_mma) {                                                                            \
-    auto kern = row_mma_kernel<FUSED, P, I>;                                                       \
+  if (a->deposit_mma && FUSED && P == PICNIX_PUSHER_BORIS && I == PICNIX_INTERP_MC) {              \
+    auto kern = row_mma_kernel<true, PICNIX_PUSHER_BORIS, PICNIX_INTERP_MC>;                       \
     PICNIX_CUDA(a, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                         (int)rowmma::SMEM_BYTES));                                 \
     kern<<<blocks, THREADS, rowmma::SMEM_BYTES, a->stream>>>(g, a->d, rc, c0, cn, delt);           \
@@ -709,25 +711,30 @@ int launch_row_kernel(picnix_arena* a, int c0, int cn, double delt)
                                         (int)SMEM_BYTES));                                         \
     kern<<<blocks, THREADS, SMEM_BYTES, a->stream>>>(g, a->d, rc, c0, cn, delt);                   \
   }
-  switch (key) {
-  case 0:
+  if constexpr (!FUSED) {
+    // deposit only: pusher and interpolation do not enter, one instantiation serves all
     PICNIX_ROW_LAUNCH(PICNIX_PUSHER_BORIS, PICNIX_INTERP_MC);
-    break;
-  case 1:
-    PICNIX_ROW_LAUNCH(PICNIX_PUSHER_BORIS, PICNIX_INTERP_WT);
-    break;
-  case 2:
-    PICNIX_ROW_LAUNCH(PICNIX_PUSHER_VAY, PICNIX_INTERP_MC);
-    break;
-  case 3:
-    PICNIX_ROW_LAUNCH(PICNIX_PUSHER_VAY, PICNIX_INTERP_WT);
-    break;
-  case 4:
-    PICNIX_ROW_LAUNCH(PICNIX_PUSHER_HIGUERA_CARY, PICNIX_INTERP_MC);
-    break;
-  default:
-    PICNIX_ROW_LAUNCH(PICNIX_PUSHER_HIGUERA_CARY, PICNIX_INTERP_WT);
-    break;
+  } else {
+    switch (key) {
+    case 0:
+      PICNIX_ROW_LAUNCH(PICNIX_PUSHER_BORIS, PICNIX_INTERP_MC);
+      break;
+    case 1:
+      PICNIX_ROW_LAUNCH(PICNIX_PUSHER_BORIS, PICNIX_INTERP_WT);
+      break;
+    case 2:
+      PICNIX_ROW_LAUNCH(PICNIX_PUSHER_VAY, PICNIX_INTERP_MC);
+      break;
+    case 3:
+      PICNIX_ROW_LAUNCH(PICNIX_PUSHER_VAY, PICNIX_INTERP_WT);
+      break;
+    case 4:
+      PICNIX_ROW_LAUNCH(PICNIX_PUSHER_HIGUERA_CARY, PICNIX_INTERP_MC);
+      break;
+    default:
+      PICNIX_ROW_LAUNCH(PICNIX_PUSHER_HIGUERA_CARY, PICNIX_INTERP_WT);
+      break;
+    }
   }
 #undef PICNIX_ROW_LAUNCH
   far_kernel<<<64, 128, 0, a->stream>>>(g, a->d, delt);

@@ -25,6 +25,14 @@
 //     row = lane/4 (+8), columns 2*(lane%4)+{0,1}) go straight to global uj with one fp64 reduction
 //     per value -- there is no per-warp current tile any more, which frees 10 KB of shared memory
 //     per warp and lets three blocks instead of two share an SM.
+//
+// MEASURED (T3D, B200, profiles/r01_row_mma_ncu.txt): correct (same parity tests), but 36.3 ms against
+// 20.9 ms of the scalar row kernel.  The run bookkeeping (a group of four particles spans a cell
+// change or a shifted window 30 % of the time), the 8 % of particles that need their own flush and
+// the eight reductions per lane and flush add more instructions (13.6 G vs 9.5 G warp instructions)
+// than the operand traffic they save (3.5 G vs 4.2 G shared wavefronts), and the padded columns
+// double the FP64 work of the deposit.  It stays selectable (option "deposit_mma") as the evidence
+// behind "no tensor cores on this path"; the scalar kernel is the product path.
 #ifndef PICNIX_B200_ROWMMA_CUH
 #define PICNIX_B200_ROWMMA_CUH
 

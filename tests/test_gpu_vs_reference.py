@@ -161,3 +161,16 @@ def test_open_boundary_drops_particles():
     assert counts_equal(gpu, ref)
     n0 = 2 * 8 * 16 ** 3
     assert problems.total_particles(gpu) < n0
+
+
+def test_mma_deposit_variant_matches_reference():
+    """The FP64-MMA formulation of the deposit (option deposit_mma; slower, kept as evidence) passes
+    the same parity bar as the scalar row kernel."""
+    ref, gpu = make_pair("t3d", perturb=None)
+    gpu.set_option("deposit_mma", 1)
+    ref.step(0.05, 10)
+    gpu.step(0.05, 10)
+    gpu.synchronize()
+    assert counts_equal(gpu, ref)
+    assert field_err(gpu, ref, FIELD_UF) < 1e-10
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-10
