@@ -220,6 +220,12 @@ def b200_main(args, rank, world):
     from picnix_b200 import capi, problems
     from picnix_b200.distributed import DistributedSim
 
+    # stdout carries exactly ONE JSON line: anything libraries print (e.g. NCCL's version banner)
+    # is sent to stderr by pointing fd 1 there; the result line is written to the saved descriptor
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -300,10 +306,29 @@ def b200_main(args, rank, world):
                        "bytes_per_step": step_bytes},
     }
 
-    # e2e: host arrays in, host arrays out, every step (rank-local arenas; N=1 only has no peers)
+    # e2e: every rank's whole state host -> device -> host around every step (pinned reference-layout
+    # arrays); max wall time over ranks, particles and bytes summed over ranks
     e2e = None
-    if not args.no_e2e and world == 1:
-        e2e = sim.measure_e2e(DELT, args.e2e_steps)
+    if not args.no_e2e:
+        res = sim.measure_e2e(DELT, args.e2e_steps, barrier=barrier)
+        te = torch.tensor([res["elapsed"], res["particles"], float(res["h2d"]), float(res["d2h"])],
+                          dtype=torch.float64, device="cuda")
+        if world > 1:
+            tm = te.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ts = te.clone()
+            dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            e_elapsed, e_np, e_h2d, e_d2h = float(tm[0]), float(ts[1]), float(ts[2]), float(ts[3])
+        else:
+            e_elapsed, e_np, e_h2d, e_d2h = (float(x) for x in te)
+        e2e = {
+            "value": e_np * res["steps"] / e_elapsed, "unit": UNIT, "h2d_bytes_per_step": int(e_h2d),
+            "d2h_bytes_per_step": int(e_d2h), "steps": res["steps"], "ms_per_step": 1e3 * e_elapsed / res["steps"],
+            "api": ("picnix_cuda_step_host" if world == 1 else
+                    "picnix_cuda_upload_state + phases (NCCL halos) + picnix_cuda_download_state on every rank")
+                   + ": pinned reference-layout host arrays (uf, ff, AoS particles in; uf, uj, ff, AoS particles "
+                     "out) every step, three-stream copy/transposition pipeline",
+        }
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -324,12 +349,12 @@ def b200_main(args, rank, world):
             "particles_before_after": [np_total, np_after_total],
             "clocks": clocks,
             "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0,
-                                                "d2h_bytes_per_step": 0, "note": "measured at N=1 only"},
+                                                "d2h_bytes_per_step": 0, "note": "skipped (--no-e2e)"},
             "gpu_launches": int(launches1 - launches0),
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
 
     if world > 1:
         dist.destroy_process_group()

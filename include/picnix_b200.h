@@ -225,6 +225,16 @@ int picnix_cuda_step_host(picnix_arena_t* arena, double delt, int32_t nstep, dou
                           double* uj, double* ff, double* xu, const int32_t* np_in,
                           const int32_t* np_cap, int32_t* np_out);
 
+/* The two halves of picnix_cuda_step_host on their own: whole-rank state transfer through the same
+ * copy/transposition pipeline.  They are the device side of the reference's snapshot and diagnostic
+ * paths (PicChunk::pack/unpack, pic/pic_chunk.cpp:59-95; nix/statehandler.hpp; pic/diag/field.hpp,
+ * particle.hpp), which read and write the host arrays -- and they work on multi-rank arenas, where
+ * the caller drives the phases between them.  upload_state leaves the particles cell-ordered. */
+int picnix_cuda_upload_state(picnix_arena_t* arena, double* uf, double* uj, double* ff, double* xu,
+                             const int32_t* np_in, const int32_t* np_cap);
+int picnix_cuda_download_state(picnix_arena_t* arena, double* uf, double* uj, double* ff,
+                               double* xu, const int32_t* np_cap, int32_t* np_out);
+
 /* page-locked host memory for the arrays handed to picnix_cuda_step_host / upload / download
  * (an xt::xtensor can adopt it through xt::adapt); PICNIX_ERR_NODEVICE without a CUDA device */
 int picnix_cuda_host_alloc(void** ptr, int64_t bytes);

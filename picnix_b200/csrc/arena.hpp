@@ -206,6 +206,10 @@ int launch_halo_begin(picnix_arena* a, int mode);
 int launch_halo_end(picnix_arena* a, int mode);
 
 void hostio_destroy(picnix_arena* a);
+int  upload_state_pipelined(picnix_arena* a, double* uf, double* uj, double* ff, double* xu,
+                            const int32_t* np_in, const int32_t* np_cap, bool with_uj);
+int  download_state_pipelined(picnix_arena* a, double* uf, double* uj, double* ff, double* xu,
+                              const int32_t* np_cap, int32_t* np_out);
 int  step_host_pipelined(picnix_arena* a, double delt, int nstep, double* uf, double* uj, double* ff,
                          double* xu, const int32_t* np_in, const int32_t* np_cap, int32_t* np_out);
 

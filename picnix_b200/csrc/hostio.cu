@@ -152,26 +152,23 @@ constexpr int TTHREADS = 256;
 
 } // namespace
 
-int step_host_pipelined(picnix_arena* a, double delt, int nstep, double* uf, double* uj, double* ff,
-                        double* xu, const int32_t* np_in, const int32_t* np_cap, int32_t* np_out)
+// common prologue: slabs, streams, page-locking of the caller's arrays
+static int hostio_prepare(picnix_arena* a, double* uf, double* uj, double* ff, double* xu,
+                          const int32_t* np_cap, HostIO** out)
 {
   const Geom&   g     = a->g;
   const int64_t ncell = g.Ng;
   int           status;
-
   if (!a->particles_allocated) {
     if ((status = picnix_cuda_set_particle_capacity(a, np_cap)) != PICNIX_OK)
       return status;
   }
   int64_t cap_total = 0, max_seg = 0;
   for (int s = 0; s < a->nseg; s++) {
-    if (np_in[s] < 0 || np_in[s] > a->seg_cap[s])
-      return fail(a, PICNIX_ERR_OVERFLOW, "step_host: np_in exceeds segment capacity");
     cap_total += np_cap[s];
     max_seg = std::max<int64_t>(max_seg, (int64_t)a->seg_cap[s] * NC);
   }
   max_seg = std::max<int64_t>(max_seg, ncell * 18);
-
   HostIO* io = nullptr;
   if ((status = hostio_get(a, max_seg, &io)) != PICNIX_OK)
     return status;
@@ -179,15 +176,31 @@ int step_host_pipelined(picnix_arena* a, double delt, int nstep, double* uf, dou
   pin_if_needed(io, uj, (size_t)g.nchunk * ncell * 4 * sizeof(double));
   pin_if_needed(io, ff, (size_t)g.nchunk * ncell * 18 * sizeof(double));
   pin_if_needed(io, xu, (size_t)cap_total * NC * sizeof(double));
+  *out = io;
+  return PICNIX_OK;
+}
+
+// host arrays -> device state; uploaded particles are counted and sorted so that pindex is valid
+int upload_state_pipelined(picnix_arena* a, double* uf, double* uj, double* ff, double* xu,
+                           const int32_t* np_in, const int32_t* np_cap, bool with_uj)
+{
+  const Geom&   g     = a->g;
+  const int64_t ncell = g.Ng;
+  int           status;
+  HostIO*       io = nullptr;
+  if ((status = hostio_prepare(a, uf, uj, ff, xu, np_cap, &io)) != PICNIX_OK)
+    return status;
+  for (int s = 0; s < a->nseg; s++)
+    if (np_in[s] < 0 || np_in[s] > a->seg_cap[s])
+      return fail(a, PICNIX_ERR_OVERFLOW, "upload_state: np_in exceeds segment capacity");
 
   PICNIX_CUDA(a, cudaStreamSynchronize(a->stream));
   for (int s = 0; s < HostIO::NSLOT; s++)
     io->used[s] = false;
 
-  // ------------------------------------------------------------------ upload
   PICNIX_CUDA(a, cudaMemcpyAsync(a->d.uf, uf, (size_t)g.nchunk * ncell * 6 * sizeof(double),
                                  cudaMemcpyHostToDevice, io->h2d));
-  if (nstep < 1)
+  if (with_uj)
     PICNIX_CUDA(a, cudaMemcpyAsync(a->d.uj, uj, (size_t)g.nchunk * ncell * 4 * sizeof(double),
                                    cudaMemcpyHostToDevice, io->h2d));
   PICNIX_CUDA(a, cudaMemcpyAsync(a->d.np, np_in, a->nseg * sizeof(int), cudaMemcpyHostToDevice,
@@ -235,23 +248,30 @@ int step_host_pipelined(picnix_arena* a, double delt, int nstep, double* uf, dou
     io->used[slot] = true;
     slot           = (slot + 1) % HostIO::NSLOT;
   }
-  // the direct copies (uf, np) must have landed before the first kernel of the step
+  // the direct copies (uf, np) must have landed before the first kernel that follows
   PICNIX_CUDA(a, cudaEventRecord(io->ev_misc, io->h2d));
   PICNIX_CUDA(a, cudaStreamWaitEvent(a->stream, io->ev_misc, 0));
   PICNIX_CUDA(a, cudaGetLastError());
 
-  // ------------------------------------------------------------------ compute
-  a->pindex_valid = false;
+  a->pindex_valid     = false;
+  a->leave_list_valid = false;
   if ((status = launch_count(a, 0, -1)) != PICNIX_OK)
     return status;
-  if ((status = launch_sort(a, 0, -1)) != PICNIX_OK)
-    return status;
-  if ((status = picnix_cuda_step(a, delt, nstep)) != PICNIX_OK)
+  return launch_sort(a, 0, -1);
+}
+
+// device state -> host arrays (np_out receives the particle counts)
+int download_state_pipelined(picnix_arena* a, double* uf, double* uj, double* ff, double* xu,
+                             const int32_t* np_cap, int32_t* np_out)
+{
+  const Geom&   g     = a->g;
+  const int64_t ncell = g.Ng;
+  int           status;
+  HostIO*       io = nullptr;
+  if ((status = hostio_prepare(a, uf, uj, ff, xu, np_cap, &io)) != PICNIX_OK)
     return status;
   if ((status = picnix_cuda_get_np(a, np_out)) != PICNIX_OK) // synchronises the compute stream
     return status;
-
-  // ------------------------------------------------------------------ download
   for (int s = 0; s < a->nseg; s++)
     if (np_out[s] > np_cap[s])
       return fail(a, PICNIX_ERR_OVERFLOW, "host particle buffer too small for the new count");
@@ -264,8 +284,8 @@ int step_host_pipelined(picnix_arena* a, double delt, int nstep, double* uf, dou
   PICNIX_CUDA(a, cudaMemcpyAsync(uj, a->d.uj, (size_t)g.nchunk * ncell * 4 * sizeof(double),
                                  cudaMemcpyDeviceToHost, io->d2h));
 
-  pieces.clear();
-  poff = 0;
+  std::vector<Piece> pieces;
+  int64_t            poff = 0;
   for (int s = 0; s < a->nseg; s++) {
     pieces.push_back({xu + poff * NC, (int64_t)np_out[s] * NC, 0, s, np_out[s]});
     poff += np_cap[s];
@@ -277,9 +297,9 @@ int step_host_pipelined(picnix_arena* a, double delt, int nstep, double* uf, dou
       pieces.push_back({ff + (int64_t)c * ncell * 18, (int64_t)n * ncell * 18, 0, -1 - c, n});
     }
   }
-  batches = make_batches(pieces, io->slab_elems);
+  auto batches = make_batches(pieces, io->slab_elems);
 
-  slot = 0;
+  int slot = 0;
   for (auto& batch : batches) {
     if (io->used[slot])
       PICNIX_CUDA(a, cudaStreamWaitEvent(a->stream, io->drained[slot], 0));
@@ -309,9 +329,38 @@ int step_host_pipelined(picnix_arena* a, double delt, int nstep, double* uf, dou
   return picnix_cuda_synchronize(a);
 }
 
+int step_host_pipelined(picnix_arena* a, double delt, int nstep, double* uf, double* uj, double* ff,
+                        double* xu, const int32_t* np_in, const int32_t* np_cap, int32_t* np_out)
+{
+  int status = upload_state_pipelined(a, uf, uj, ff, xu, np_in, np_cap, nstep < 1);
+  if (status != PICNIX_OK)
+    return status;
+  if ((status = picnix_cuda_step(a, delt, nstep)) != PICNIX_OK)
+    return status;
+  return download_state_pipelined(a, uf, uj, ff, xu, np_cap, np_out);
+}
+
 } // namespace picnix
 
 extern "C" {
+
+int picnix_cuda_upload_state(picnix_arena_t* a, double* uf, double* uj, double* ff, double* xu,
+                             const int32_t* np_in, const int32_t* np_cap)
+{
+  if (a == nullptr || uf == nullptr || uj == nullptr || ff == nullptr || xu == nullptr ||
+      np_in == nullptr || np_cap == nullptr)
+    return PICNIX_ERR_INVALID;
+  return picnix::upload_state_pipelined(a, uf, uj, ff, xu, np_in, np_cap, true);
+}
+
+int picnix_cuda_download_state(picnix_arena_t* a, double* uf, double* uj, double* ff, double* xu,
+                               const int32_t* np_cap, int32_t* np_out)
+{
+  if (a == nullptr || uf == nullptr || uj == nullptr || ff == nullptr || xu == nullptr ||
+      np_cap == nullptr || np_out == nullptr)
+    return PICNIX_ERR_INVALID;
+  return picnix::download_state_pipelined(a, uf, uj, ff, xu, np_cap, np_out);
+}
 
 int picnix_cuda_host_alloc(void** ptr, int64_t bytes)
 {

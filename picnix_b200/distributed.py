@@ -151,28 +151,41 @@ class DistributedSim(CudaSim):
             self.step_phases(dt)
 
     # -- end-to-end measurement through the host-buffer entry point -----------------------------
-    def measure_e2e(self, dt, nstep):
-        """particle-steps/s through picnix_cuda_step_host: host arrays in and out every step."""
+    def measure_e2e(self, dt, nstep, barrier=None):
+        """Time `nstep` steps with the rank's whole state crossing the host boundary every step.
+
+        One rank: picnix_cuda_step_host.  Several ranks: picnix_cuda_upload_state, the phases with
+        the NCCL transport between boundary_begin/end, picnix_cuda_download_state -- the same
+        pipeline, with the inter-GPU halos in the middle.  Returns this rank's wall time and byte
+        counts; the caller takes the max / sums over ranks."""
         import torch
 
-        assert self.world == 1
         st = self.host_state(pinned=True)  # outside the timed region
         np_now = st["np"].copy()
         fields = st["uf"].nbytes + st["uj"].nbytes + st["ff"].nbytes
+
+        def one_step():
+            if self.world == 1:
+                self.step_host(st, dt, 1)
+                return fields - st["uj"].nbytes  # uj is an output only
+            self.upload_state(st)
+            self.step_phases(dt)
+            self.download_state(st)
+            return fields
+
+        one_step()  # untimed: allocates the slabs and streams of the pipeline
         h2d = d2h = 0
-        self.step_host(st, dt, 1)  # untimed: allocates the slabs and streams of the pipeline
         torch.cuda.synchronize()
+        if barrier is not None:
+            barrier()
         t0 = time.perf_counter()
         for _ in range(nstep):
-            h2d += fields - st["uj"].nbytes + int(st["np"].sum()) * 56  # uj is an output only
-            self.step_host(st, dt, 1)
+            n_in = int(st["np"].sum())
+            h2d += one_step() + n_in * 56
             d2h += fields + int(st["np"].sum()) * 56
         torch.cuda.synchronize()
+        if barrier is not None:
+            barrier()
         elapsed = time.perf_counter() - t0
-        return {
-            "value": float(np_now.sum()) * nstep / elapsed, "unit": "particle-steps/s",
-            "h2d_bytes_per_step": h2d // nstep, "d2h_bytes_per_step": d2h // nstep, "steps": nstep,
-            "ms_per_step": 1e3 * elapsed / nstep,
-            "api": "picnix_cuda_step_host: pinned reference-layout host arrays (uf, ff, AoS particles in; uf, uj, "
-                   "ff, AoS particles out) every step, three-stream copy/transposition pipeline",
-        }
+        return {"elapsed": elapsed, "particles": float(np_now.sum()), "h2d": h2d // nstep, "d2h": d2h // nstep,
+                "steps": nstep}

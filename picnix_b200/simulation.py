@@ -279,6 +279,20 @@ class CudaSim:
         st["np"] = np_out
         return st
 
+    def upload_state(self, st):
+        """picnix_cuda_upload_state: whole-rank host arrays -> device (particles end up cell-ordered)."""
+        self.commit()
+        self._check(self.lib.picnix_cuda_upload_state(self.h, st["uf"], st["uj"], st["ff"], st["xu"], st["np"],
+                                                      st["caps"]))
+
+    def download_state(self, st):
+        """picnix_cuda_download_state: device -> the same host arrays; st['np'] gets the new counts."""
+        np_out = np.zeros_like(st["np"])
+        self._check(self.lib.picnix_cuda_download_state(self.h, st["uf"], st["uj"], st["ff"], st["xu"],
+                                                        st["caps"], np_out))
+        st["np"] = np_out
+        return st
+
     @staticmethod
     def host_particles(st, Ns, ic, isp):
         seg = ic * Ns + isp

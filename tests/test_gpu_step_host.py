@@ -66,3 +66,24 @@ def test_host_alloc_roundtrip():
     p = C.c_void_p()
     assert lib.picnix_cuda_host_alloc(C.byref(p), 1 << 20) == capi.OK and p.value
     assert lib.picnix_cuda_host_free(p) == capi.OK
+
+
+def test_upload_download_state_roundtrip():
+    """picnix_cuda_upload_state / download_state (the snapshot path): a state downloaded from one
+    arena and uploaded into a fresh one continues to the same result."""
+    _, a = make_pair("t3d", perturb=None)
+    _, b = make_pair("t3d", perturb=None, seed=11)   # different initial particles: must be overwritten
+    a.step(0.05, 3)
+    st = a.host_state(pinned=True)
+    a.download_state(st)
+    b.upload_state(st)
+    a.step(0.05, 3)
+    b.step(0.05, 3)
+    a.synchronize()
+    b.synchronize()
+    for ic in range(a.nchunk):
+        fa, fb = a.get_field(ic, FIELD_UF), b.get_field(ic, FIELD_UF)
+        assert np.max(np.abs(fa - fb)) <= 1e-11 * np.max(np.abs(fa))
+        for isp in range(a.Ns):
+            assert a.get_np(ic, isp) == b.get_np(ic, isp)
+            assert np.array_equal(a.get_pindex(ic, isp), b.get_pindex(ic, isp))
