@@ -1,0 +1,100 @@
+"""GPU parity on the edge cases of the path (against the compiled reference):
+ragged and empty particle segments, particles that move more than one cell in a step (the
+far-mover list of the tiled kernel), every pusher / interpolation variant of the tiled fused
+kernel over several steps at relativistic temperature, and a step on a state without particles."""
+import numpy as np
+import pytest
+
+from helpers import FIELD_UF, FIELD_UJ, counts_equal, field_err, keys_equal, particle_err
+from oracle import ref_backend
+from picnix_b200 import problems
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_backend.available(), reason="oracle/_ref not built")]
+
+
+def make_pair(ndims, cdims, species, ppc, cc, thin=None, order=2, pusher=0, interp=0, B0=(5.0, 0.0, 0.0), seed=5):
+    """Reference and CUDA arenas with identical state; `thin(chunk id, species)` -> number of
+    particles to keep in that segment (None keeps all)."""
+    from picnix_b200 import CudaSim
+
+    kw = dict(Ns=len(species), cc=cc, delh=1.0, order=order, pusher=pusher, interp=interp)
+    sims = [ref_backend.RefSim(ndims, cdims, vector_mode=1, **kw), CudaSim(ndims, cdims, **kw)]
+    dims = problems.chunk_dims(ndims, cdims)
+    for sim in sims:
+        _, coord = sim.chunkmap()
+        for isp, (q, m) in enumerate(problems.species_charge_mass(species, ppc)):
+            sim.set_species(isp, q, m)
+        nb = sim.nb
+        for ic in range(sim.nchunk):
+            uf = np.zeros(sim.shape + (6,), dtype=np.float64)
+            uf[nb:nb + dims[0], nb:nb + dims[1], nb:nb + dims[2], 3:6] = B0
+            sim.set_field(ic, FIELD_UF, uf)
+            parts = problems.make_chunk_particles(ic, coord[ic], dims, 1.0, species, ppc, seed)
+            for isp, xu in enumerate(parts):
+                keep = xu.shape[0] if thin is None else thin(ic, isp, xu.shape[0])
+                # capacity as for the full segment, so that arrivals fit
+                sim.set_particles(ic, isp, xu[:keep], np_alloc=int(xu.shape[0] * 1.5))
+        sim.finalize_setup()
+    return sims
+
+
+def test_ragged_and_empty_segments():
+    def thin(ic, isp, n):
+        if ic % 3 == 0:
+            return 0                    # chunk without any particle
+        if isp == 1 and ic % 2 == 1:
+            return 7                    # nearly empty species
+        return n - (13 * ic) % 50       # ragged
+    ref, gpu = make_pair((16, 16, 16), (2, 2, 2), problems.THERMAL_SPECIES, (8, 8), 10.0, thin=thin)
+    ref.step(0.05, 12)
+    gpu.step(0.05, 12)
+    gpu.synchronize()
+    assert counts_equal(gpu, ref)
+    assert field_err(gpu, ref, FIELD_UF) < 1e-10
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-10
+    dx, du, same = particle_err(gpu, ref, scale_x=16.0, scale_u=10.0)
+    assert same and dx < 1e-11 and du < 1e-11
+
+
+def test_no_particles_at_all():
+    ref, gpu = make_pair((16, 16, 16), (2, 2, 2), problems.THERMAL_SPECIES, (4, 4), 10.0,
+                         thin=lambda ic, isp, n: 0)
+    ref.step(0.05, 3)
+    gpu.step(0.05, 3)
+    gpu.synchronize()
+    assert counts_equal(gpu, ref)
+    assert problems.total_particles(gpu) == 0
+    assert field_err(gpu, ref, FIELD_UF) < 1e-13
+
+
+def test_fused_kernel_far_movers():
+    """dt large enough that many particles cross more than one cell: the tiled kernel hands them to
+    its far-mover list; current, keys and phase space must still match the reference."""
+    ref, gpu = make_pair((16, 16, 16), (2, 2, 2), problems.THERMAL_SPECIES, (8, 8), 10.0)
+    dt = 0.9
+    ref.push_velocity(dt)
+    ref.push_position(dt)
+    ref.deposit_current(dt)
+    gpu.push_deposit_fused(dt)
+    dx, du, same = particle_err(gpu, ref, scale_x=16.0, scale_u=10.0)
+    assert same and dx < 1e-14 and du < 1e-13
+    assert keys_equal(gpu, ref)
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-12
+
+
+@pytest.mark.parametrize("pusher,interp", [(0, 1), (1, 0), (1, 1), (2, 0), (2, 1)])
+def test_tiled_kernel_variants_relativistic_multistep(pusher, interp):
+    """Vay / Higuera-Cary pushers and WT interpolation through the tiled fused kernel, at a
+    relativistic temperature (u ~ c), over several steps."""
+    species = [dict(qm=-1.0, ro=1.0, vt=1.0), dict(qm=+0.1, ro=10.0, vt=0.3)]
+    ref, gpu = make_pair((16, 16, 16), (2, 2, 2), species, (8, 8), 1.0, pusher=pusher, interp=interp,
+                         B0=(0.5, 0.2, 0.0))
+    dt = 0.4  # c dt / dx = 0.4 < 1/sqrt(3)
+    ref.step(dt, 8)
+    gpu.step(dt, 8)
+    gpu.synchronize()
+    assert counts_equal(gpu, ref)
+    assert field_err(gpu, ref, FIELD_UF) < 1e-10
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-10
+    dx, du, same = particle_err(gpu, ref, scale_x=16.0, scale_u=1.0)
+    assert same and dx < 1e-11 and du < 1e-10
