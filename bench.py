@@ -272,8 +272,13 @@ def b200_main(args, rank, world):
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     sim.synchronize()  # raises on device-side overflow flags
     np_after = int(sim.get_np_all().sum())
+    # size-independent checks of the timed state: charge conservation residuals (signed sums per
+    # chunk like PicChunk::get_diverror, worst chunk reported)
+    de = sim.get_diverror()
+    div_e_worst, div_b_worst = float(np.abs(de[:, 0]).max()), float(np.abs(de[:, 1]).max())
 
-    t = torch.tensor([elapsed_ms, float(np_local), float(np_after), kernel_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([elapsed_ms, float(np_local), float(np_after), kernel_ms, div_e_worst, div_b_worst],
+                     dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -281,6 +286,7 @@ def b200_main(args, rank, world):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         elapsed_ms = float(tmax[0])
         kernel_ms = float(tmax[3])
+        div_e_worst, div_b_worst = float(tmax[4]), float(tmax[5])
         np_total = float(tsum[1])
         np_after_total = float(tsum[2])
     else:
@@ -347,6 +353,8 @@ def b200_main(args, rank, world):
             "config": workload_config(args, world),
             "per_gpu": value / world,
             "particles_before_after": [np_total, np_after_total],
+            "conservation": {"particles_conserved": np_total == np_after_total,
+                             "max_chunk_abs_sum_divE_minus_rho": div_e_worst, "max_chunk_abs_sum_divB": div_b_worst},
             "clocks": clocks,
             "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0,
                                                 "d2h_bytes_per_step": 0, "note": "skipped (--no-e2e)"},
