@@ -98,3 +98,47 @@ def test_tiled_kernel_variants_relativistic_multistep(pusher, interp):
     assert field_err(gpu, ref, FIELD_UJ) < 1e-10
     dx, du, same = particle_err(gpu, ref, scale_x=16.0, scale_u=1.0)
     assert same and dx < 1e-11 and du < 1e-10
+
+
+def make_cherenkov_pair(ndims, cdims, nppc=16, u0=0.1, vt=0.1, delh=0.1, cc=1.0, order=2, seed=9):
+    """example/cherenkov (main.cpp:31-160, config.toml): pair plasma (mime = 1) drifting with u0 along
+    x, cell size delh = 0.1 (NOT 1), cc = 1, wp = 1: me = 1/nppc, qe = -wp/nppc*sqrt(gamma)."""
+    from picnix_b200 import CudaSim
+
+    gamma = np.sqrt(1 + u0 * u0 / (cc * cc))
+    me = 1.0 / nppc
+    qe = -1.0 / nppc * np.sqrt(gamma)
+    kw = dict(Ns=2, cc=cc, delh=delh, order=order, pusher=0, interp=0)
+    sims = [ref_backend.RefSim(ndims, cdims, vector_mode=1, **kw), CudaSim(ndims, cdims, **kw)]
+    dims = problems.chunk_dims(ndims, cdims)
+    species = [dict(qm=1.0, ro=1.0, vt=vt, drift=(u0, 0.0, 0.0)), dict(qm=1.0, ro=1.0, vt=vt, drift=(u0, 0.0, 0.0))]
+    for sim in sims:
+        _, coord = sim.chunkmap()
+        sim.set_species(0, qe, me)
+        sim.set_species(1, -qe, me)
+        for ic in range(sim.nchunk):
+            sim.set_field(ic, FIELD_UF, np.zeros(sim.shape + (6,), dtype=np.float64))
+            parts = problems.make_chunk_particles(ic, coord[ic], dims, delh, species, (nppc, nppc), seed)
+            for isp, xu in enumerate(parts):
+                sim.set_particles(ic, isp, xu)
+        sim.finalize_setup()
+    return sims
+
+
+@pytest.mark.parametrize("ndims,cdims", [((1, 32, 32), (1, 2, 2)), ((16, 16, 16), (2, 2, 2))])
+def test_cherenkov_like_small_cells(ndims, cdims):
+    """BASELINE configs[2]: cell size 0.1, c = 1, drifting pair plasma; 2-D (generic kernels) and the
+    same in 3-D (tiled kernel) -- catches any place that assumes unit cells."""
+    ref, gpu = make_cherenkov_pair(ndims, cdims)
+    dt = 0.05
+    ref.step(dt, 20)
+    gpu.step(dt, 20)
+    gpu.synchronize()
+    assert counts_equal(gpu, ref)
+    assert field_err(gpu, ref, FIELD_UF) < 1e-10
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-10
+    L = 0.1 * max(ndims)
+    dx, du, same = particle_err(gpu, ref, scale_x=L, scale_u=1.0)
+    assert same and dx < 1e-11 and du < 1e-10
+    de_ref, de_gpu = ref.get_diverror().sum(0), gpu.get_diverror().sum(0)
+    assert abs(de_gpu[0]) < 1e-9 and abs(de_ref[0]) < 1e-9
