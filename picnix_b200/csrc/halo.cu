@@ -212,7 +212,9 @@ remote_halo_kernel(Geom g, double* __restrict__ field, const int* __restrict__ d
     if (IS_PACK) {
       msg[e] = field[c * ncomp + k];
     } else if (IS_CURRENT) {
-      field[c * ncomp + k] += msg[e];
+      // the margins of a face, its edges and its corners overlap and every message is its own
+      // thread block: the add must be atomic (a plain += loses updates between messages)
+      atomicAdd(field + c * ncomp + k, msg[e]);
     } else {
       field[c * ncomp + k] = msg[e];
     }
