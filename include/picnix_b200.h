@@ -235,6 +235,19 @@ int picnix_cuda_upload_state(picnix_arena_t* arena, double* uf, double* uj, doub
 int picnix_cuda_download_state(picnix_arena_t* arena, double* uf, double* uj, double* ff,
                                double* xu, const int32_t* np_cap, int32_t* np_out);
 
+/* ---- chunk moves between ranks (Application::rebalance, nix/application.hpp:332) ------------- */
+/*
+ * PicChunk::get_size_byte / pack / unpack (pic/pic_chunk.cpp:25-95) with the packed chunk kept in
+ * DEVICE memory: fields (uf, uj, Friedman history) and the particles of every species of one local
+ * chunk as one contiguous buffer that the caller hands to NCCL / a peer copy.  The receiving arena
+ * is created with the new rank boundary (picnix_assign_rebalance) and capacities >= the incoming
+ * counts; after all chunks arrived the caller runs picnix_cuda_sort_particle once.
+ */
+int picnix_cuda_chunk_pack_size(picnix_arena_t* arena, int32_t ichunk, int64_t* bytes);
+int picnix_cuda_chunk_pack(picnix_arena_t* arena, int32_t ichunk, void* dev_buf, int64_t bytes);
+int picnix_cuda_chunk_unpack(picnix_arena_t* arena, int32_t ichunk, const void* dev_buf,
+                             int64_t bytes);
+
 /* page-locked host memory for the arrays handed to picnix_cuda_step_host / upload / download
  * (an xt::xtensor can adopt it through xt::adapt); PICNIX_ERR_NODEVICE without a CUDA device */
 int picnix_cuda_host_alloc(void** ptr, int64_t bytes);

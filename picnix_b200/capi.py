@@ -97,6 +97,9 @@ SIGNATURES = {
     "picnix_cuda_step_host": (_i32, [_vp, _dbl, _i32, _pd, _pd, _pd, _pd, _pi, _pi, _pi]),
     "picnix_cuda_upload_state": (_i32, [_vp, _pd, _pd, _pd, _pd, _pi, _pi]),
     "picnix_cuda_download_state": (_i32, [_vp, _pd, _pd, _pd, _pd, _pi, _pi]),
+    "picnix_cuda_chunk_pack_size": (_i32, [_vp, _i32, C.POINTER(_i64)]),
+    "picnix_cuda_chunk_pack": (_i32, [_vp, _i32, _vp, _i64]),
+    "picnix_cuda_chunk_unpack": (_i32, [_vp, _i32, _vp, _i64]),
     "picnix_cuda_host_alloc": (_i32, [C.POINTER(_vp), _i64]),
     "picnix_cuda_host_free": (_i32, [_vp]),
 }

@@ -126,6 +126,40 @@ def exchange(sim, transport, mode):
     sim.boundary_end(mode)
 
 
+def _owner(boundary, gid):
+    return int(np.searchsorted(np.asarray(boundary), gid, side="right") - 1)
+
+
+def _capacities(np_rows, ratio):
+    """segment capacities for incoming chunks: the reference's (1 + buffer_ratio) slack plus room
+    for one allocation unit, so that a freshly moved chunk can still receive migrants"""
+    return (np_rows.astype(np.float64) * (1 + ratio)).astype(np.int32).reshape(-1) + 256
+
+
+def rebalance_in_process(sims, new_boundary, make_sim):
+    """Application::rebalance for R arenas living in ONE process (tests; single-node tools).
+
+    `sims[r]` owns the chunk ids [b[r], b[r+1]); `new_boundary` comes from Balancer::assign
+    (capi.assign_rebalance / assign_initial).  Every chunk is packed on its old owner
+    (PicChunk::pack -> picnix_cuda_chunk_pack), handed over as a device buffer and unpacked on its
+    new owner; new arenas are created by `make_sim(rank, boundary)`.  Returns the new arenas."""
+    nrank = len(sims)
+    old_boundary = [s.chunk_id_begin for s in sims] + [sims[-1].chunk_id_begin + sims[-1].nchunk]
+    np_all = np.concatenate([s.get_np_all() for s in sims], axis=0)
+    new = [make_sim(r, new_boundary) for r in range(nrank)]
+    for r, t in enumerate(new):
+        t.set_capacity(_capacities(np_all[new_boundary[r]:new_boundary[r + 1]], t.cfg.buffer_ratio))
+        for isp, (q, m) in sims[0]._species.items():
+            t.set_species(isp, q, m)
+    for gid in range(old_boundary[-1]):
+        src, dst = _owner(old_boundary, gid), _owner(new_boundary, gid)
+        buf = sims[src].chunk_pack(gid - old_boundary[src])
+        new[dst].chunk_unpack(gid - new_boundary[dst], buf)
+    for t in new:
+        t.sort_particle()  # keys + pindex of the arrived particles
+    return new
+
+
 class DistributedSim(CudaSim):
     """CudaSim whose chunk ids are split over `world` ranks like the reference's MPI ranks."""
 
@@ -149,6 +183,53 @@ class DistributedSim(CudaSim):
             return super().step(dt, nstep)
         for _ in range(nstep):
             self.step_phases(dt)
+
+    def rebalanced(self, new_boundary):
+        """Application::rebalance across GPUs: returns a NEW DistributedSim that owns the chunk range
+        `new_boundary[rank] .. new_boundary[rank+1]`; chunks that change owner travel packed
+        (picnix_cuda_chunk_pack) over NCCL send/recv, device to device."""
+        import torch
+        import torch.distributed as dist
+
+        new_boundary = [int(b) for b in new_boundary]
+        mine = torch.zeros((self.cfg.cdims[0] * self.cfg.cdims[1] * self.cfg.cdims[2], self.Ns), dtype=torch.int64,
+                           device="cuda")
+        mine[self.chunk_id_begin:self.chunk_id_begin + self.nchunk] = torch.from_numpy(
+            self.get_np_all().astype(np.int64)).cuda()
+        if self.world > 1:
+            dist.all_reduce(mine)  # every chunk has exactly one owner: sum == gather
+        np_all = mine.cpu().numpy()
+        old_boundary = [0] * (self.world + 1)
+        ob = torch.zeros(self.world + 1, dtype=torch.int64, device="cuda")
+        ob[self.rank] = self.chunk_id_begin
+        if self.rank == self.world - 1:
+            ob[self.world] = self.chunk_id_begin + self.nchunk
+        if self.world > 1:
+            dist.all_reduce(ob)
+        old_boundary = [int(v) for v in ob.cpu()]
+
+        new = DistributedSim(rank=self.rank, world=self.world, boundary=new_boundary, **self._ctor)
+        new.set_capacity(_capacities(np_all[new_boundary[self.rank]:new_boundary[self.rank + 1]],
+                                     self.cfg.buffer_ratio))
+        for isp, (q, m) in self._species.items():
+            new.set_species(isp, q, m)
+        for gid in range(old_boundary[-1]):
+            src, dst = _owner(old_boundary, gid), _owner(new_boundary, gid)
+            if src == self.rank:
+                buf = self.chunk_pack(gid - old_boundary[src])
+                if dst == self.rank:
+                    new.chunk_unpack(gid - new_boundary[dst], buf)
+                else:
+                    dist.send(torch.tensor([buf.numel()], dtype=torch.int64, device="cuda"), dst)
+                    dist.send(buf, dst)
+            elif dst == self.rank:
+                n = torch.zeros(1, dtype=torch.int64, device="cuda")
+                dist.recv(n, src)
+                buf = torch.empty(int(n.item()), dtype=torch.uint8, device="cuda")
+                dist.recv(buf, src)
+                new.chunk_unpack(gid - new_boundary[dst], buf)
+        new.sort_particle()
+        return new
 
     # -- end-to-end measurement through the host-buffer entry point -----------------------------
     def measure_e2e(self, dt, nstep, barrier=None):

@@ -57,6 +57,10 @@ class CudaSim:
         self.Ng = Ng.value
         self._pending = {}
         self._capacity_set = False
+        self._species = {}
+        self._ctor = dict(ndims=tuple(ndims), cdims=tuple(cdims), Ns=Ns, cc=cc, delh=delh, order=order,
+                          pusher=pusher, interp=interp, periodic=tuple(periodic), friedman=friedman,
+                          buffer_ratio=buffer_ratio)
 
     # -- plumbing --------------------------------------------------------------------------
     def _check(self, status):
@@ -104,7 +108,29 @@ class CudaSim:
         return self.shape + tail
 
     def set_species(self, isp, q, m):
+        self._species[isp] = (q, m)
         self._check(self.lib.picnix_cuda_set_species(self.h, isp, q, m))
+
+    def set_capacity(self, caps):
+        """XtensorParticle::allocate for every (chunk, species) segment at once."""
+        caps = np.ascontiguousarray(caps, dtype=np.int32).reshape(-1)
+        assert caps.size == self.nchunk * self.Ns
+        self._check(self.lib.picnix_cuda_set_particle_capacity(self.h, caps))
+        self._capacity_set = True
+
+    # -- chunk moves (rebalancing): the whole state of a local chunk as one device buffer --------
+    def chunk_pack(self, ic):
+        import torch
+
+        self.commit()
+        n = C.c_int64()
+        self._check(self.lib.picnix_cuda_chunk_pack_size(self.h, ic, C.byref(n)))
+        buf = torch.empty(n.value, dtype=torch.uint8, device="cuda")
+        self._check(self.lib.picnix_cuda_chunk_pack(self.h, ic, C.c_void_p(buf.data_ptr()), n.value))
+        return buf
+
+    def chunk_unpack(self, ic, buf):
+        self._check(self.lib.picnix_cuda_chunk_unpack(self.h, ic, C.c_void_p(buf.data_ptr()), buf.numel()))
 
     def set_field(self, ic, which, arr):
         arr = np.ascontiguousarray(arr, dtype=np.float64)

@@ -146,3 +146,50 @@ def test_ranks_on_one_device_equal_single_arena(ndims, cdims, nrank):
         for ic in range(s.nchunk):
             a, b = s.get_field(ic, 3), single.get_field(s.chunk_id_begin + ic, 3)
             assert np.max(np.abs(a - b)) <= 1e-11 * np.max(np.abs(b))
+
+
+def test_rebalance_moves_chunks_between_arenas():
+    """start from an even split of a non-uniform plasma, run, let the balancer move
+    the rank boundaries on the particle loads, move the chunks (pack -> device buffer -> unpack),
+    continue -- the result equals the single-arena run."""
+    from picnix_b200 import CudaSim
+    from picnix_b200.distributed import rebalance_in_process
+
+    ndims, cdims, nrank = (1, 32, 32), (1, 4, 4), 3
+    species, ppc, B0, dt = problems.THERMAL_SPECIES, (8, 8), (5.0, 0.0, 0.0), 0.05
+    kw = dict(Ns=2, cc=10.0, delh=1.0, order=2)
+    single = CudaSim(ndims, cdims, **kw)
+    fill(single, ndims, cdims, species, ppc, B0)
+    single.exchange(MODE_EMF)
+
+    even = capi.assign_initial(np.ones(single.nchunk), nrank)
+    sims = [CudaSim(ndims, cdims, nrank=nrank, rank=r, boundary=even, **kw) for r in range(nrank)]
+    for s in sims:
+        fill(s, ndims, cdims, species, ppc, B0)
+    exchange_all(sims, MODE_EMF)
+    for _ in range(5):
+        step_all(sims, dt)
+
+    loads = np.concatenate([s.get_np_all().sum(axis=1) for s in sims]).astype(np.float64)
+    balanced = capi.assign_initial(loads, nrank)
+    assert not np.array_equal(balanced, even)            # the sheet makes the even split unbalanced
+    assert np.array_equal(capi.assign_rebalance(loads, even).shape, even.shape)
+    sims = rebalance_in_process(sims, balanced,
+                                lambda r, b: CudaSim(ndims, cdims, nrank=nrank, rank=r, boundary=b, **kw))
+    per_rank = [float(s.get_np_all().sum()) for s in sims]
+    assert max(per_rank) / (sum(per_rank) / nrank) < 1.35  # balanced on particle count
+    for _ in range(5):
+        step_all(sims, dt)
+
+    single.step(dt, 10)
+    single.synchronize()
+    for s in sims:
+        s.synchronize()
+        for ic in range(s.nchunk):
+            gid = s.chunk_id_begin + ic
+            for which in (0, 1):
+                a, b = s.get_field(ic, which), single.get_field(gid, which)
+                assert np.max(np.abs(a - b)) <= 1e-11 * max(np.max(np.abs(b)), 1e-300), (gid, which)
+            for isp in range(2):
+                assert s.get_np(ic, isp) == single.get_np(gid, isp)
+                assert np.array_equal(s.get_pindex(ic, isp), single.get_pindex(gid, isp))
