@@ -57,9 +57,21 @@ class Transport:
         self.device = "cuda" if device_buffers else "cpu"
         self.peers = sim.peers() if world > 1 else []
 
+    def _shares_stream(self):
+        """True when the arena enqueues on the stream torch (and therefore NCCL) orders against."""
+        if self.device != "cuda":
+            return True
+        import torch
+
+        return getattr(self.sim, "_stream_ptr", None) == torch.cuda.current_stream().cuda_stream
+
     def _exchange(self, pairs):
         import torch.distributed as dist
 
+        shared = self._shares_stream()
+        if not shared:
+            # the arena packs on its own stream: NCCL must not read the buffers before that is done
+            self.sim.synchronize()
         ops = []
         for peer, send, recv in pairs:
             if recv.numel() > 0:
@@ -69,6 +81,11 @@ class Transport:
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
+        if not shared:
+            # ... and the arena must not unpack before the data has landed
+            import torch
+
+            torch.cuda.current_stream().synchronize()
 
     def move(self, mode):
         """Between boundary_begin(mode) and boundary_end(mode): send -> peer's recv buffer."""

@@ -58,6 +58,7 @@ class CudaSim:
         self._pending = {}
         self._capacity_set = False
         self._species = {}
+        self._stream_ptr = None  # the arena owns its stream until set_stream() is called
         self._ctor = dict(ndims=tuple(ndims), cdims=tuple(cdims), Ns=Ns, cc=cc, delh=delh, order=order,
                           pusher=pusher, interp=interp, periodic=tuple(periodic), friedman=friedman,
                           buffer_ratio=buffer_ratio)
@@ -86,6 +87,7 @@ class CudaSim:
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.picnix_cuda_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+        self._stream_ptr = int(cuda_stream_ptr)
 
     def counters(self):
         launches, pushes = C.c_int64(), C.c_int64()
