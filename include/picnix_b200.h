@@ -106,8 +106,13 @@ int picnix_cuda_arena_create(const picnix_config_t* cfg, const int32_t* boundary
 int picnix_cuda_arena_destroy(picnix_arena_t* arena);
 const char* picnix_cuda_last_error(const picnix_arena_t* arena);
 
-/* tuning / testing switches: "force_generic" = 1 bypasses the tiled 3-D kernels (row-owner
- * deposit) so the thread-per-particle kernels run instead */
+/* tuning / testing switches:
+ *   "force_generic" = 1  bypasses the tiled 3-D kernels (row-owner deposit): the thread-per-particle
+ *                        kernels run instead
+ *   "lazy_sort"     = 0  the counting sort always moves the particles (default 1: when the tiled
+ *                        fused kernel will consume the result only the permutation is written and
+ *                        the reordering rides on the next push; results are identical)
+ *   "deposit_mma"   = 1  FP64-MMA formulation of the deposit (slower; kept as measured evidence) */
 int picnix_cuda_set_option(picnix_arena_t* arena, const char* key, int64_t value);
 
 /* use an existing CUDA stream (cudaStream_t as void*); default is a stream the arena owns */

@@ -75,6 +75,11 @@ int upload_particles(picnix_arena* a, int ichunk, int is, const double* aos, int
   if (np < 0 || np > a->seg_cap[seg])
     return fail(a, PICNIX_ERR_OVERFLOW, "upload_particles: np exceeds segment capacity");
 
+  {
+    int mstatus = materialize_sort(a);
+    if (mstatus != PICNIX_OK)
+      return mstatus;
+  }
   a->pindex_valid = false; // the new particles are not cell-ordered until the next sort
   a->leave_list_valid = false;
   int64_t elems = (int64_t)np * NC;
@@ -112,8 +117,10 @@ int download_particles(picnix_arena* a, int ichunk, int is, int which, int n, do
     return PICNIX_OK;
 
   int64_t elems  = (int64_t)n * NC;
-  int     status = ensure_stage(a, elems);
+  int     status = materialize_sort(a);
   if (status != PICNIX_OK)
+    return status;
+  if ((status = ensure_stage(a, elems)) != PICNIX_OK)
     return status;
   const double* soa     = which == 0 ? a->d.xu : a->d.xv;
   int           threads = 256;
@@ -371,6 +378,8 @@ int picnix_cuda_arena_create(const picnix_config_t* cfg, const int32_t* boundary
   // tuning/testing override of the row-kernel variant (same as set_option("deposit_mma"))
   if (const char* env = std::getenv("PICNIX_DEPOSIT_MMA"))
     a->deposit_mma = std::atoi(env) != 0;
+  if (const char* env = std::getenv("PICNIX_LAZY_SORT"))
+    a->lazy_sort = std::atoi(env) != 0;
   a->cfg = *cfg;
   std::memset(&a->g, 0, sizeof(a->g));
   std::memset(&a->d, 0, sizeof(a->d));
@@ -444,6 +453,7 @@ int picnix_cuda_arena_destroy(picnix_arena_t* a)
   dev_free(a->d.xu);
   dev_free(a->d.xv);
   dev_free(a->d.gindex);
+  dev_free(a->d.perm);
   dev_free(a->d.seg_off);
   dev_free(a->d.seg_cap);
   dev_free(a->d.np);
@@ -573,9 +583,11 @@ int picnix_cuda_set_particle_capacity(picnix_arena_t* a, const int32_t* np_alloc
   dev_free(a->d.xu);
   dev_free(a->d.xv);
   dev_free(a->d.gindex);
+  dev_free(a->d.perm);
   dev_free(a->d.leave_count);
   dev_free(a->d.leave_idx);
   a->leave_list_valid = false;
+  a->perm_pending     = false;
 
   int64_t total = 0;
   for (int s = 0; s < a->nseg; s++) {
@@ -595,6 +607,8 @@ int picnix_cuda_set_particle_capacity(picnix_arena_t* a, const int32_t* np_alloc
   if ((status = dev_alloc(a, &a->d.xv, (size_t)total * NC)) != PICNIX_OK)
     return status;
   if ((status = dev_alloc(a, &a->d.gindex, (size_t)total)) != PICNIX_OK)
+    return status;
+  if ((status = dev_alloc(a, &a->d.perm, (size_t)total, false)) != PICNIX_OK)
     return status;
   // a quarter of the population leaving in one step is far beyond any Courant-limited run; the
   // migration falls back to scanning the keys if the list overflows
@@ -673,6 +687,11 @@ int picnix_cuda_download_gindex(picnix_arena_t* a, int32_t ichunk, int32_t is, i
   int seg = ichunk * a->g.Ns + is;
   if (n < 0 || n > a->seg_cap[seg])
     return PICNIX_ERR_INVALID;
+  {
+    int mstatus = materialize_sort(a);
+    if (mstatus != PICNIX_OK)
+      return mstatus;
+  }
   PICNIX_CUDA(a, cudaStreamSynchronize(a->stream));
   PICNIX_CUDA(a, cudaMemcpy(gindex, a->d.gindex + a->seg_off[seg], n * sizeof(int),
                             cudaMemcpyDeviceToHost));

@@ -61,6 +61,7 @@ struct DevPtrs {
   double*  xu;       // [7][pcap]  SoA particle buffer "xu"
   double*  xv;       // [7][pcap]  SoA particle buffer "xv"
   int*     gindex;   // [pcap] cell key of xu
+  int*     perm;     // [pcap] lazy sort: sorted slot -> slot the particle still sits in (per segment)
   int64_t  pcap;     // component stride of xu/xv
   int64_t* seg_off;  // [nseg] first slot of segment (chunk*Ns + species)
   int*     seg_cap;  // [nseg] capacity
@@ -145,6 +146,8 @@ struct picnix_arena {
   bool                   particles_allocated = false;
   bool                   pindex_valid = false;  // pindex matches the particle order (after a sort)
   bool                   leave_list_valid = false; // DevPtrs::leave_idx describes the current keys
+  bool                   lazy_sort    = true;   // option "lazy_sort": allow index-only sorts (see sort.cu)
+  bool                   perm_pending = false;  // xu is NOT yet in pindex order: DevPtrs::perm holds the order
   bool                   force_generic = false; // testing: bypass the tiled kernels
   bool                   deposit_mma   = false; // row kernel variant: deposit through the FP64 MMA unit
   int64_t                kernel_launches = 0;
@@ -193,6 +196,7 @@ int launch_deposit_current(picnix_arena* a, int c0, int cn, double delt);
 int launch_push_deposit_fused(picnix_arena* a, int c0, int cn, double delt);
 int launch_deposit_rows(picnix_arena* a, int c0, int cn, double delt);
 bool row_kernel_applies(const picnix_arena* a);
+bool row_geometry_applies(const picnix_arena* a);
 
 int ensure_moment_array(picnix_arena* a);
 int launch_deposit_moment(picnix_arena* a);
@@ -201,6 +205,7 @@ int launch_particle_energy(picnix_arena* a, double* particle);
 
 int launch_count(picnix_arena* a, int c0, int cn);
 int launch_sort(picnix_arena* a, int c0, int cn);
+int materialize_sort(picnix_arena* a); // physically order xu if an index-only sort is pending
 
 int launch_halo_begin(picnix_arena* a, int mode);
 int launch_halo_end(picnix_arena* a, int mode);

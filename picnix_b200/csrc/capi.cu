@@ -31,6 +31,11 @@ int picnix_cuda_set_option(picnix_arena_t* a, const char* key, int64_t value)
     a->force_generic = value != 0;
     return PICNIX_OK;
   }
+  if (std::string(key) == "lazy_sort") {
+    int status = materialize_sort(a);
+    a->lazy_sort = value != 0;
+    return status;
+  }
   if (std::string(key) == "deposit_mma") {
     a->deposit_mma = value != 0;
     return PICNIX_OK;

@@ -59,6 +59,11 @@ int picnix_cuda_chunk_pack(picnix_arena_t* a, int32_t ichunk, void* dev_buf, int
     return fail(a, PICNIX_ERR_INVALID, "no particles allocated");
   const Geom&      g = a->g;
   std::vector<int> np(g.Ns);
+  {
+    int mstatus = materialize_sort(a);
+    if (mstatus != PICNIX_OK)
+      return mstatus;
+  }
   PICNIX_CUDA(a, cudaStreamSynchronize(a->stream));
   PICNIX_CUDA(a, cudaMemcpy(np.data(), a->d.np + (size_t)ichunk * g.Ns, g.Ns * sizeof(int),
                             cudaMemcpyDeviceToHost));
@@ -101,6 +106,11 @@ int picnix_cuda_chunk_unpack(picnix_arena_t* a, int32_t ichunk, const void* dev_
     return PICNIX_ERR_INVALID;
   if (!a->particles_allocated)
     return fail(a, PICNIX_ERR_INVALID, "chunk_unpack: set_particle_capacity first");
+  {
+    int mstatus = materialize_sort(a);
+    if (mstatus != PICNIX_OK)
+      return mstatus;
+  }
   const Geom&          g = a->g;
   std::vector<int64_t> header(4 + g.Ns, 0);
   if (bytes < (int64_t)(header.size() * sizeof(int64_t)))

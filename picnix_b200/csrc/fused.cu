@@ -158,7 +158,13 @@ int launch_push_deposit_fused(picnix_arena* a, int c0, int cn, double delt)
   a->leave_list_valid = (c0 == 0 && cn == g.nchunk);
 
   if (row_kernel_applies(a))
-    return launch_row_fused(a, c0, cn, delt);
+    return launch_row_fused(a, c0, cn, delt); // consumes a pending index-only sort itself
+
+  {
+    int mstatus = materialize_sort(a); // a pending index-only sort must be made physical first
+    if (mstatus != PICNIX_OK)
+      return mstatus;
+  }
 
   int maxcap = 0;
   for (int s = c0 * g.Ns; s < (c0 + cn) * g.Ns; s++)

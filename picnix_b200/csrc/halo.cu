@@ -592,6 +592,8 @@ int launch_halo_begin(picnix_arena* a, int mode)
     int status = ensure_particle_staging(a);
     if (status != PICNIX_OK)
       return status;
+    if ((status = materialize_sort(a)) != PICNIX_OK)
+      return status;
     for (auto& p : a->peers)
       PICNIX_CUDA(a, cudaMemsetAsync(p.d_psend_count, 0, sizeof(int), a->stream));
     int maxcap = 0;

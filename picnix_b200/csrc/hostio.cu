@@ -255,6 +255,7 @@ int upload_state_pipelined(picnix_arena* a, double* uf, double* uj, double* ff, 
 
   a->pindex_valid     = false;
   a->leave_list_valid = false;
+  a->perm_pending     = false; // the arrays were overwritten: nothing left to reorder
   if ((status = launch_count(a, 0, -1)) != PICNIX_OK)
     return status;
   return launch_sort(a, 0, -1);
@@ -269,6 +270,8 @@ int download_state_pipelined(picnix_arena* a, double* uf, double* uj, double* ff
   int           status;
   HostIO*       io = nullptr;
   if ((status = hostio_prepare(a, uf, uj, ff, xu, np_cap, &io)) != PICNIX_OK)
+    return status;
+  if ((status = materialize_sort(a)) != PICNIX_OK)
     return status;
   if ((status = picnix_cuda_get_np(a, np_out)) != PICNIX_OK) // synchronises the compute stream
     return status;

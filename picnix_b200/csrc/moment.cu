@@ -317,6 +317,8 @@ int launch_deposit_moment(picnix_arena* a)
   int status = ensure_moment_array(a);
   if (status != PICNIX_OK)
     return status;
+  if ((status = materialize_sort(a)) != PICNIX_OK)
+    return status;
   const Geom& g = a->g;
   // fill_all(um, 0), pic/engine/moment.hpp:104,166
   PICNIX_CUDA(a, cudaMemsetAsync(a->d.um, 0, (size_t)g.nchunk * g.Ng * g.Ns * NMOM * sizeof(double),

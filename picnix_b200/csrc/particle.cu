@@ -230,6 +230,11 @@ void launch_deposit_order(picnix_arena* a, int c0, int cn, int bps, double delt)
 int launch_push_velocity(picnix_arena* a, int c0, int cn, double delt)
 {
   resolve_range(a, c0, cn);
+  {
+    int mstatus = materialize_sort(a); // a pending index-only sort must be made physical first
+    if (mstatus != PICNIX_OK)
+      return mstatus;
+  }
   if (!a->particles_allocated)
     return fail(a, PICNIX_ERR_INVALID, "no particles allocated");
   int bps = blocks_per_segment(a, c0, cn);
@@ -253,6 +258,11 @@ int launch_push_velocity(picnix_arena* a, int c0, int cn, double delt)
 int launch_push_position(picnix_arena* a, int c0, int cn, double delt)
 {
   resolve_range(a, c0, cn);
+  {
+    int mstatus = materialize_sort(a); // a pending index-only sort must be made physical first
+    if (mstatus != PICNIX_OK)
+      return mstatus;
+  }
   if (!a->particles_allocated)
     return fail(a, PICNIX_ERR_INVALID, "no particles allocated");
   int bps = blocks_per_segment(a, c0, cn);
@@ -270,6 +280,11 @@ int launch_push_position(picnix_arena* a, int c0, int cn, double delt)
 int launch_count(picnix_arena* a, int c0, int cn)
 {
   resolve_range(a, c0, cn);
+  {
+    int mstatus = materialize_sort(a); // a pending index-only sort must be made physical first
+    if (mstatus != PICNIX_OK)
+      return mstatus;
+  }
   if (!a->particles_allocated)
     return fail(a, PICNIX_ERR_INVALID, "no particles allocated");
   int bps = blocks_per_segment(a, c0, cn);
@@ -287,6 +302,11 @@ int launch_count(picnix_arena* a, int c0, int cn)
 int launch_deposit_current(picnix_arena* a, int c0, int cn, double delt)
 {
   resolve_range(a, c0, cn);
+  {
+    int mstatus = materialize_sort(a); // a pending index-only sort must be made physical first
+    if (mstatus != PICNIX_OK)
+      return mstatus;
+  }
   if (!a->particles_allocated)
     return fail(a, PICNIX_ERR_INVALID, "no particles allocated");
   if (cn == 0)

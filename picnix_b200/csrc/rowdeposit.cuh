@@ -84,7 +84,20 @@ struct WarpSmem {
   double stg[32 * REC];
   double tile[TILE];
   int    info[32];
+  int    pbuf[32]; // lazy sort: permutation entries of the next batch, filled by cp.async
 };
+
+// asynchronous 4-byte global -> shared copy: no register, hence no scoreboard dependency between the
+// permutation entry and the particle loads it feeds until the explicit wait
+__device__ __forceinline__ void cp_async_i32(int* smem, const int* gmem)
+{
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait()
+{
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
 constexpr size_t SMEM_BYTES = sizeof(double) * FTILE + sizeof(WarpSmem) * WARPS;
 

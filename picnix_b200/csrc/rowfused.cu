@@ -88,7 +88,10 @@ __device__ __forceinline__ double interp27(const double* __restrict__ p, const d
   return rz;
 }
 
-template <bool FUSED, int Pusher, int Interp>
+// PERM (fused only): a lazy sort is pending -- sorted slot j of a segment still sits in slot perm[j] of
+// xu; the kernel reads through the permutation and writes the pushed particle (all seven components)
+// to slot j of xv, so the reordering costs no pass of its own (the host swaps xu/xv afterwards).
+template <bool FUSED, int Pusher, int Interp, bool PERM>
 __global__ void __launch_bounds__(THREADS, 2)
 row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
 {
@@ -171,9 +174,11 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
 
     // the six phase-space components of the NEXT batch are requested before phase 2 of the current
     // one, so their HBM latency is hidden behind the accumulation loop
-    double pfx = 0, pfy = 0, pfz = 0, pfux = 0, pfuy = 0, pfuz = 0;
+    double pfx = 0, pfy = 0, pfz = 0, pfux = 0, pfuy = 0, pfuz = 0, pfid = 0;
     if (FUSED && pb + lane < pe) {
-      const int64_t i = off + pb + lane;
+      const int64_t i = PERM ? off + d.perm[off + pb + lane] : off + pb + lane;
+      if (PERM)
+        pfid = d.xu[6 * d.pcap + i];
       pfx  = d.xu[0 * d.pcap + i];
       pfy  = d.xu[1 * d.pcap + i];
       pfz  = d.xu[2 * d.pcap + i];
@@ -184,6 +189,10 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
 
     for (int base = pb; base < pe; base += 32) {
       const int n = min(32, pe - base);
+      // PERM: the permutation entries of the next batch travel global -> shared asynchronously while
+      // phase 1 runs; they are read (and the particle loads issued) after phase 1
+      if (PERM && base + 32 + lane < pe)
+        cp_async_i32(ws->pbuf + lane, d.perm + off + base + 32 + lane);
 
       // ---------------- phase 1: one particle per lane ----------------
       int inf = 0;
@@ -247,12 +256,15 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
           y1 = y0;
           z1 = z0;
           push_position(x1, y1, z1, ux, uy, uz, rc.rc, delt);
-          d.xu[0 * d.pcap + i] = x1;
-          d.xu[1 * d.pcap + i] = y1;
-          d.xu[2 * d.pcap + i] = z1;
-          d.xu[3 * d.pcap + i] = ux;
-          d.xu[4 * d.pcap + i] = uy;
-          d.xu[5 * d.pcap + i] = uz;
+          double* xo = PERM ? d.xv : d.xu; // i is the SORTED slot: in place, or the other buffer
+          xo[0 * d.pcap + i] = x1;
+          xo[1 * d.pcap + i] = y1;
+          xo[2 * d.pcap + i] = z1;
+          xo[3 * d.pcap + i] = ux;
+          xo[4 * d.pcap + i] = uy;
+          xo[5 * d.pcap + i] = uz;
+          if (PERM)
+            xo[6 * d.pcap + i] = pfid;
         } else {
           x0 = d.xv[0 * d.pcap + i];
           y0 = d.xv[1 * d.pcap + i];
@@ -299,8 +311,14 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
         }
       }
       ws->info[lane] = inf;
+      if (PERM) {
+        cp_async_commit_wait();
+        __syncwarp();
+      }
       if (FUSED && base + 32 + lane < pe) {
-        const int64_t i = off + base + 32 + lane;
+        const int64_t i = PERM ? off + ws->pbuf[lane] : off + base + 32 + lane;
+        if (PERM)
+          pfid = d.xu[6 * d.pcap + i];
         pfx  = d.xu[0 * d.pcap + i];
         pfy  = d.xu[1 * d.pcap + i];
         pfz  = d.xu[2 * d.pcap + i];
@@ -684,6 +702,14 @@ int launch_row_kernel(picnix_arena* a, int c0, int cn, double delt)
   const Geom& g      = a->g;
   const int   blocks = g.dims[0] * (g.dims[1] / WARPS) * (g.dims[2] / RX) * cn;
   const int   key    = FUSED ? a->cfg.pusher * 2 + a->cfg.interp : 0;
+  // a pending lazy sort is consumed by the fused kernel itself when it covers the whole arena;
+  // everything else (partial ranges, deposit only, the MMA experiment) wants physically ordered arrays
+  const bool  perm   = FUSED && a->perm_pending && c0 == 0 && cn == g.nchunk && !a->deposit_mma;
+  if (!perm) {
+    int status = materialize_sort(a);
+    if (status != PICNIX_OK)
+      return status;
+  }
 
   RowConst rc;
   for (int i = 0; i < 3; i++) {
@@ -705,8 +731,13 @@ int launch_row_kernel(picnix_arena* a, int c0, int cn, double delt)
     PICNIX_CUDA(a, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                         (int)rowmma::SMEM_BYTES));                                 \
     kern<<<blocks, THREADS, rowmma::SMEM_BYTES, a->stream>>>(g, a->d, rc, c0, cn, delt);           \
+  } else if (perm) {                                                                               \
+    auto kern = row_kernel<FUSED, P, I, FUSED>;                                                    \
+    PICNIX_CUDA(a, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                        (int)SMEM_BYTES));                                         \
+    kern<<<blocks, THREADS, SMEM_BYTES, a->stream>>>(g, a->d, rc, c0, cn, delt);                   \
   } else {                                                                                         \
-    auto kern = row_kernel<FUSED, P, I>;                                                           \
+    auto kern = row_kernel<FUSED, P, I, false>;                                                    \
     PICNIX_CUDA(a, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                         (int)SMEM_BYTES));                                         \
     kern<<<blocks, THREADS, SMEM_BYTES, a->stream>>>(g, a->d, rc, c0, cn, delt);                   \
@@ -739,6 +770,11 @@ int launch_row_kernel(picnix_arena* a, int c0, int cn, double delt)
 #undef PICNIX_ROW_LAUNCH
   far_kernel<<<64, 128, 0, a->stream>>>(g, a->d, delt);
   a->kernel_launches += 2;
+  if (perm) {
+    // the kernel wrote the pushed particles in sorted order into xv
+    std::swap(a->d.xu, a->d.xv);
+    a->perm_pending = false;
+  }
   return check_cuda(a, cudaGetLastError(), "row_kernel");
 }
 
@@ -747,11 +783,16 @@ int launch_row_kernel(picnix_arena* a, int c0, int cn, double delt)
 // The row-owner kernel needs 3-D, 2nd-order shapes, rows that split into RX-cell segments and
 // WARPS-row groups, and a pindex that describes the current particle order (set by the sort,
 // cleared by uploads).
-bool row_kernel_applies(const picnix_arena* a)
+bool row_geometry_applies(const picnix_arena* a)
 {
   const Geom& g = a->g;
   return g.dimension == 3 && g.order == 2 && (g.dims[2] % rowdep::RX) == 0 &&
-         (g.dims[1] % rowdep::WARPS) == 0 && a->pindex_valid && !a->force_generic;
+         (g.dims[1] % rowdep::WARPS) == 0;
+}
+
+bool row_kernel_applies(const picnix_arena* a)
+{
+  return row_geometry_applies(a) && a->pindex_valid && !a->force_generic;
 }
 
 int launch_deposit_rows(picnix_arena* a, int c0, int cn, double delt)

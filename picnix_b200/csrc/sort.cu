@@ -12,6 +12,14 @@
 //   1. exclusive scan of the per-segment histogram pcount -> pindex, and pcount <- pindex (cursor)
 //   2. scatter xu -> xv with one atomic cursor bump per particle (order inside a cell is free)
 //   3. Np <- pindex[Ng], tail counter <- 0; the host swaps the xu/xv pointers
+//
+// Lazy variant (option "lazy_sort", on by default, used when the tiled push kernel will consume the
+// result): step 2 writes only the permutation `perm[sorted slot] = current slot` (8 B per particle
+// instead of 116 B).  The next fused push reads its particles through `perm` and writes them to
+// the other buffer in sorted order, so the physical reordering rides on traffic the push has
+// anyway.  Any other consumer of the particle arrays (downloads, the generic kernels, moments,
+// chunk moves) first calls materialize_sort(), which performs the gather the scatter would have
+// done.  pindex, Np and the per-cell particle sets are identical in both variants.
 #include "arena.hpp"
 
 namespace picnix
@@ -111,6 +119,51 @@ scatter_kernel(Geom g, DevPtrs d, int seg0, int blocks_per_seg)
     d.xv[k * d.pcap + off + dst] = d.xu[k * d.pcap + off + ip];
 }
 
+// lazy sort: same cursor logic, but only the permutation is written
+__global__ void __launch_bounds__(SCATTER_THREADS)
+scatter_index_kernel(Geom g, DevPtrs d, int seg0, int blocks_per_seg)
+{
+  const int lseg = blockIdx.x / blocks_per_seg;
+  const int b    = blockIdx.x - lseg * blocks_per_seg;
+  const int seg  = seg0 + lseg;
+  const int ip   = b * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int n    = min(d.np[seg] + d.ntail[seg], d.seg_cap[seg]);
+  if (b * (int)blockDim.x + (int)(threadIdx.x & ~31u) >= n)
+    return;
+
+  const int64_t off  = d.seg_off[seg];
+  const int     key  = ip < n ? d.gindex[off + ip] : g.Ng;
+  const bool    keep = key < g.Ng;
+
+  const unsigned peers  = __match_any_sync(0xffffffffu, key);
+  const int      leader = __ffs(peers) - 1;
+  int            base   = 0;
+  if (keep && lane == leader)
+    base = atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (!keep)
+    return;
+  d.perm[off + base + __popc(peers & ((1u << lane) - 1u))] = ip;
+}
+
+// materialise a pending lazy sort: xv[sorted slot] <- xu[perm[sorted slot]]
+__global__ void __launch_bounds__(SCATTER_THREADS)
+gather_kernel(Geom g, DevPtrs d, int seg0, int blocks_per_seg)
+{
+  const int lseg = blockIdx.x / blocks_per_seg;
+  const int b    = blockIdx.x - lseg * blocks_per_seg;
+  const int seg  = seg0 + lseg;
+  const int j    = b * blockDim.x + threadIdx.x;
+  if (j >= d.np[seg])
+    return;
+  const int64_t off = d.seg_off[seg];
+  const int     src = d.perm[off + j];
+#pragma unroll
+  for (int k = 0; k < NC; k++)
+    d.xv[k * d.pcap + off + j] = d.xu[k * d.pcap + off + src];
+}
+
 __global__ void finish_kernel(Geom g, DevPtrs d, int seg0, int nseg)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,6 +180,12 @@ __global__ void finish_kernel(Geom g, DevPtrs d, int seg0, int nseg)
 int launch_sort(picnix_arena* a, int c0, int cn)
 {
   resolve_range(a, c0, cn);
+  {
+    // a sort on top of a pending index sort (e.g. count + sort after a step): order physically first
+    int status = materialize_sort(a);
+    if (status != PICNIX_OK)
+      return status;
+  }
   if (!a->particles_allocated)
     return fail(a, PICNIX_ERR_INVALID, "no particles allocated");
   if (cn == 0)
@@ -146,18 +205,46 @@ int launch_sort(picnix_arena* a, int c0, int cn)
   for (int s = seg0; s < seg0 + nseg; s++)
     maxcap = std::max(maxcap, a->seg_cap[s]);
   int bps = (maxcap + SCATTER_THREADS - 1) / SCATTER_THREADS;
+  // the tiled push kernel reads through the permutation: no need to move the particles now
+  const bool lazy = a->lazy_sort && !a->force_generic && row_geometry_applies(a);
   if (bps > 0) {
-    scatter_kernel<<<bps * nseg, SCATTER_THREADS, 0, a->stream>>>(g, a->d, seg0, bps);
+    if (lazy)
+      scatter_index_kernel<<<bps * nseg, SCATTER_THREADS, 0, a->stream>>>(g, a->d, seg0, bps);
+    else
+      scatter_kernel<<<bps * nseg, SCATTER_THREADS, 0, a->stream>>>(g, a->d, seg0, bps);
     a->kernel_launches++;
   }
   finish_kernel<<<(nseg + 127) / 128, 128, 0, a->stream>>>(g, a->d, seg0, nseg);
   a->kernel_launches++;
   PICNIX_CUDA(a, cudaGetLastError());
 
-  // XtensorParticle::swap (nix/xtensor_particle.hpp:120-123)
-  std::swap(a->d.xu, a->d.xv);
+  if (lazy) {
+    a->perm_pending = true;
+  } else {
+    // XtensorParticle::swap (nix/xtensor_particle.hpp:120-123)
+    std::swap(a->d.xu, a->d.xv);
+  }
   a->pindex_valid     = true;
   a->leave_list_valid = false; // slots changed
+  return PICNIX_OK;
+}
+
+int materialize_sort(picnix_arena* a)
+{
+  if (!a->perm_pending)
+    return PICNIX_OK;
+  const Geom& g      = a->g;
+  int         maxcap = 0;
+  for (int s = 0; s < a->nseg; s++)
+    maxcap = std::max(maxcap, a->seg_cap[s]);
+  const int bps = (maxcap + SCATTER_THREADS - 1) / SCATTER_THREADS;
+  if (bps > 0) {
+    gather_kernel<<<bps * a->nseg, SCATTER_THREADS, 0, a->stream>>>(g, a->d, 0, bps);
+    a->kernel_launches++;
+  }
+  PICNIX_CUDA(a, cudaGetLastError());
+  std::swap(a->d.xu, a->d.xv);
+  a->perm_pending = false;
   return PICNIX_OK;
 }
 
