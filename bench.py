@@ -16,8 +16,9 @@ field halo, counting sort.  Weak scaling: every GPU owns its own 128^3 block of 
 `e2e`      : the same metric through picnix_cuda_step_host (HOST arrays in the reference's layouts
              in, HOST arrays out, every step), i.e. what a host-resident PicChunk would see.
 `roofline` : the fused push+deposit kernel against the measured HBM copy bandwidth
-             (MEASURED_PEAKS.json), algorithmic bytes = 116 B/particle (R 56 + W 56 + 4 B key) plus
-             the field tile traffic per cell.
+             (MEASURED_PEAKS.json), algorithmic bytes = 120 B/particle (R 56 + 4 B permutation + W 56
+             + 4 B key) plus the field tile traffic per cell; `traffic` = DRAM bytes of one
+             launch from the committed ncu capture.
 `cpu_baseline` / `--impl reference` : the UNMODIFIED reference (oracle/_ref, its own OpenMP loop
              over chunks and xsimd kernels) on all host cores, on a bounded sample of the workload.
 """
@@ -44,7 +45,7 @@ CHUNK = 16
 PPC = (32, 32)
 
 # algorithmic bytes (DESIGN.md "Kernels and rooflines")
-BYTES_PUSH_PER_PARTICLE = 56 + 56 + 4          # fused push+deposit: read xu, write xu, write key
+BYTES_PUSH_PER_PARTICLE = 56 + 56 + 4 + 4      # fused push+deposit: read xu (+4 B permutation), write, write key
 BYTES_PUSH_PER_CELL = 48 + 2 * 32              # field tile read + J accumulate (RMW) per cell
 BYTES_STEP_PER_PARTICLE = 232                  # push pass + sort pass
 BYTES_STEP_PER_CELL = 600
