@@ -338,7 +338,7 @@ def b200_main(args, rank, world):
         }
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:  # the CPU baseline is timed at N=1 only
         try:
             res = run_reference(args.ref_cells, args.ppc, 5, 1)
             cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",

@@ -29,23 +29,26 @@ namespace
 constexpr int MTHREADS = 128;
 constexpr int NMOM     = 14;
 
+// rg = 1/gamma is formed once; the reference divides by gamma in every term, which differs by an ulp
+// (far inside the 1e-12 summation-order tolerance) and costs ten fp64 divisions per particle and point
 __device__ __forceinline__ void moment_terms(double ww, double ux, double uy, double uz, double gm,
-                                             double cc, double* t)
+                                             double rg, double cc, double* t)
 {
+  const double wg = ww * rg;
   t[0]  = ww;
-  t[1]  = ww * ux / gm;
-  t[2]  = ww * uy / gm;
-  t[3]  = ww * uz / gm;
+  t[1]  = wg * ux;
+  t[2]  = wg * uy;
+  t[3]  = wg * uz;
   t[4]  = ww * gm * cc;
-  t[5]  = ww * ux * ux / gm;
-  t[6]  = ww * uy * uy / gm;
-  t[7]  = ww * uz * uz / gm;
+  t[5]  = wg * ux * ux;
+  t[6]  = wg * uy * uy;
+  t[7]  = wg * uz * uz;
   t[8]  = ww * ux;
   t[9]  = ww * uy;
   t[10] = ww * uz;
-  t[11] = ww * ux * uy / gm;
-  t[12] = ww * uy * uz / gm;
-  t[13] = ww * uz * ux / gm;
+  t[11] = wg * ux * uy;
+  t[12] = wg * uy * uz;
+  t[13] = wg * uz * ux;
 }
 
 // weights and first stencil index of one axis (BaseMoment::local{1,2,3}d, moment.hpp:219-395)
@@ -94,7 +97,7 @@ moment_generic_kernel(Geom g, DevPtrs d, int blocks_per_seg)
         if (Dim >= 3)
           ww = ww * wz[jz];
         double t[NMOM];
-        moment_terms(ww, ux, uy, uz, gm, g.cc, t);
+        moment_terms(ww, ux, uy, uz, gm, 1 / gm, g.cc, t);
         double* m = um + ((((int64_t)(iz0 + jz) * g.M[1] + iy0 + jy) * g.M[2] + ix0 + jx) * g.Ns + is) * NMOM;
 #pragma unroll
         for (int k = 0; k < NMOM; k++)
@@ -150,6 +153,7 @@ moment_cell_kernel(Geom g, DevPtrs d)
     const int64_t i  = off + ip;
     const double  ux = d.xu[3 * d.pcap + i], uy = d.xu[4 * d.pcap + i], uz = d.xu[5 * d.pcap + i];
     const double  gm = sqrt(1 + (ux * ux + uy * uy + uz * uz) * rc * rc);
+    const double  rg = 1 / gm;
     double        wx[N], wy[N], wz[N];
     moment_axis<Order>(d.xu[0 * d.pcap + i], lim[4], g.del[2], g.Lb[2], wx);
     double ww = ms * pick(wx, px, N);
@@ -162,7 +166,7 @@ moment_cell_kernel(Geom g, DevPtrs d)
       ww = ww * pick(wz, pz, N);
     }
     double t[NMOM];
-    moment_terms(ww, ux, uy, uz, gm, g.cc, t);
+    moment_terms(ww, ux, uy, uz, gm, rg, g.cc, t);
 #pragma unroll
     for (int k = 0; k < NMOM; k++)
       acc[k] += t[k];
