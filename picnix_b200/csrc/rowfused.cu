@@ -160,11 +160,31 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
   const double xigrid = xmin + 0.5 * dx, yigrid = ymin + 0.5 * dy, zigrid = zmin + 0.5 * dz;
   const int    key0 = jz * g.fsz + jy * g.fsy + jx0;
 
+  // Particle range of the first species; inside the loop the range of the NEXT species is requested
+  // at the top of the current one, and its first batch is prefetched during the last batch of the
+  // current one, so that a warp meets the global-memory latency only once per row segment.
+  int64_t off;
+  int     pb, pe;
+  {
+    const int  seg0 = chunk * g.Ns;
+    const int* pix0 = d.pindex + (int64_t)seg0 * (g.Ng + 1);
+    off             = d.seg_off[seg0];
+    pb              = pix0[key0];
+    pe              = pix0[key0 + RX];
+  }
+  bool   primed = false; // the first batch of the current species is already in the pf* registers
+  double pfx = 0, pfy = 0, pfz = 0, pfux = 0, pfuy = 0, pfuz = 0, pfid = 0;
+
   for (int is = 0; is < g.Ns; is++) {
-    const int     seg = chunk * g.Ns + is;
-    const int64_t off = d.seg_off[seg];
-    const int*    pix = d.pindex + (int64_t)seg * (g.Ng + 1);
-    const int     pb = pix[key0], pe = pix[key0 + RX];
+    const int seg = chunk * g.Ns + is;
+    int64_t   noff = 0;
+    int       npb = 0, npe = 0;
+    if (is + 1 < g.Ns) {
+      const int* pix1 = d.pindex + (int64_t)(seg + 1) * (g.Ng + 1);
+      noff            = d.seg_off[seg + 1];
+      npb             = pix1[key0];
+      npe             = pix1[key0 + RX];
+    }
     const double  q    = d.qm[2 * is];
     const double  qmdt = 0.5 * q / d.qm[2 * is + 1] * delt;
 
@@ -174,8 +194,7 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
 
     // the six phase-space components of the NEXT batch are requested before phase 2 of the current
     // one, so their HBM latency is hidden behind the accumulation loop
-    double pfx = 0, pfy = 0, pfz = 0, pfux = 0, pfuy = 0, pfuz = 0, pfid = 0;
-    if (FUSED && pb + lane < pe) {
+    if (FUSED && !primed && pb + lane < pe) {
       const int64_t i = PERM ? off + d.perm[off + pb + lane] : off + pb + lane;
       if (PERM)
         pfid = d.xu[6 * d.pcap + i];
@@ -189,10 +208,16 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
 
     for (int base = pb; base < pe; base += 32) {
       const int n = min(32, pe - base);
-      // PERM: the permutation entries of the next batch travel global -> shared asynchronously while
-      // phase 1 runs; they are read (and the particle loads issued) after phase 1
-      if (PERM && base + 32 + lane < pe)
-        cp_async_i32(ws->pbuf + lane, d.perm + off + base + 32 + lane);
+      // the batch whose data is requested after phase 1: the next one of this species, or the first
+      // one of the next species
+      const bool    last  = base + 32 >= pe;
+      const int64_t xoff  = last ? noff : off;
+      const int     xbase = last ? npb : base + 32;
+      const int     xend  = last ? npe : pe;
+      // PERM: its permutation entries travel global -> shared asynchronously while phase 1 runs; they
+      // are read (and the particle loads issued) after phase 1
+      if (PERM && xbase + lane < xend)
+        cp_async_i32(ws->pbuf + lane, d.perm + xoff + xbase + lane);
 
       // ---------------- phase 1: one particle per lane ----------------
       int inf = 0;
@@ -315,8 +340,8 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
         cp_async_commit_wait();
         __syncwarp();
       }
-      if (FUSED && base + 32 + lane < pe) {
-        const int64_t i = PERM ? off + ws->pbuf[lane] : off + base + 32 + lane;
+      if (FUSED && xbase + lane < xend) {
+        const int64_t i = PERM ? xoff + ws->pbuf[lane] : xoff + xbase + lane;
         if (PERM)
           pfid = d.xu[6 * d.pcap + i];
         pfx  = d.xu[0 * d.pcap + i];
@@ -384,6 +409,10 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
         flush(ws->tile, acc, a, b, curinfo & 0xff, 1, 1, 1);
       __syncwarp();
     }
+    primed = FUSED && pe > pb; // the last batch requested the first one of the next species
+    off    = noff;
+    pb     = npb;
+    pe     = npe;
   }
 
   // warp tile -> global current: one fp64 reduction per non-zero tile value
