@@ -214,6 +214,36 @@ def gpu_layout(ngpu):
     return {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}[ngpu]
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs of the NUMA node its GPU
+    hangs off, so that the host<->device copies of the e2e measurement do not cross sockets.
+    Best effort: any failure leaves the affinity untouched."""
+    try:
+        import torch
+
+        prop = torch.cuda.get_device_properties(local_rank)
+        if all(hasattr(prop, k) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        else:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i",
+                                  str(local_rank)], stdout=subprocess.PIPE, text=True).stdout.strip()
+            bdf = out.lower().replace("00000000:", "0000:")
+        node = int(open(f"/sys/bus/pci/devices/{bdf.lower()}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def b200_main(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -229,6 +259,7 @@ def b200_main(args, rank, world):
 
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
