@@ -128,6 +128,36 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
   double*       uj  = d.uj + (int64_t)chunk * g.Ng * 4;
   const int     My = g.M[1], Mx = g.M[2];
 
+  // ---- particle range of the first species and its first batch: requested BEFORE the field tile is
+  // staged, so that the dependent chain pindex -> permutation -> particle data overlaps the tile loads
+  const int key0 = jz * g.fsz + jy * g.fsy + jx0;
+  // (inside the species loop the range of the NEXT species is requested at the top of the current
+  // one, and its first batch during the last batch of the current one)
+  int64_t off;
+  int     pb, pe;
+  {
+    const int  seg0 = chunk * g.Ns;
+    const int* pix0 = d.pindex + (int64_t)seg0 * (g.Ng + 1);
+    off             = d.seg_off[seg0];
+    pb              = pix0[key0];
+    pe              = pix0[key0 + RX];
+  }
+  bool   primed = false; // the first batch of the current species is already in the pf* registers
+  double pfx = 0, pfy = 0, pfz = 0, pfux = 0, pfuy = 0, pfuz = 0, pfid = 0;
+
+  if (FUSED && pb + lane < pe) {
+    const int64_t i = PERM ? off + d.perm[off + pb + lane] : off + pb + lane;
+    if (PERM)
+      pfid = d.xu[6 * d.pcap + i];
+    pfx    = d.xu[0 * d.pcap + i];
+    pfy    = d.xu[1 * d.pcap + i];
+    pfz    = d.xu[2 * d.pcap + i];
+    pfux   = d.xu[3 * d.pcap + i];
+    pfuy   = d.xu[4 * d.pcap + i];
+    pfuz   = d.xu[5 * d.pcap + i];
+  }
+  primed = FUSED && pe > pb;
+
   // ---- stage the field tile (global layout [z][y][x][6], 16-byte copies) ----
   if (FUSED) {
     const double* uf = d.uf + (int64_t)chunk * g.Ng * 6;
@@ -158,22 +188,6 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
   const double yh0 = ymin + (double)jy * dy, yh1 = ymin + (double)(jy + 1) * dy;
   const double zh0 = zmin + (double)jz * dz, zh1 = zmin + (double)(jz + 1) * dz;
   const double xigrid = xmin + 0.5 * dx, yigrid = ymin + 0.5 * dy, zigrid = zmin + 0.5 * dz;
-  const int    key0 = jz * g.fsz + jy * g.fsy + jx0;
-
-  // Particle range of the first species; inside the loop the range of the NEXT species is requested
-  // at the top of the current one, and its first batch is prefetched during the last batch of the
-  // current one, so that a warp meets the global-memory latency only once per row segment.
-  int64_t off;
-  int     pb, pe;
-  {
-    const int  seg0 = chunk * g.Ns;
-    const int* pix0 = d.pindex + (int64_t)seg0 * (g.Ng + 1);
-    off             = d.seg_off[seg0];
-    pb              = pix0[key0];
-    pe              = pix0[key0 + RX];
-  }
-  bool   primed = false; // the first batch of the current species is already in the pf* registers
-  double pfx = 0, pfy = 0, pfz = 0, pfux = 0, pfuy = 0, pfuz = 0, pfid = 0;
 
   for (int is = 0; is < g.Ns; is++) {
     const int seg = chunk * g.Ns + is;
