@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=128, help="cells per GPU per dimension")
     ap.add_argument("--ppc", type=int, default=32, help="particles per cell per species")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-cells", type=int, default=64, help="cells per dimension of the CPU sample")
