@@ -180,6 +180,7 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
     __syncwarp();
 
   const double xmin = lim[4], ymin = lim[2], zmin = lim[0];
+  const double xmax = lim[5], ymax = lim[3], zmax = lim[1]; // in registers: the key tests run per particle
   const double rdx = rc.rd[2], rdy = rc.rd[1], rdz = rc.rd[0];
   const double dx = rc.del[2], dy = rc.del[1], dz = rc.del[0];
   // cell-centre ("integer") and cell-edge ("half") grid points of this row, pic/engine/velocity.hpp:304-315
@@ -324,9 +325,9 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
         const int iz1 = digitize(z1, zmin, rdz);
         if (FUSED) {
           int key = iz1 * g.fsz + iy1 * g.fsy + ix1;
-          key     = (x1 < xmin || x1 >= lim[5]) ? g.Ng : key;
-          key     = (y1 < ymin || y1 >= lim[3]) ? g.Ng : key;
-          key     = (z1 < zmin || z1 >= lim[1]) ? g.Ng : key;
+          key     = (x1 < xmin || x1 >= xmax) ? g.Ng : key;
+          key     = (y1 < ymin || y1 >= ymax) ? g.Ng : key;
+          key     = (z1 < zmin || z1 >= zmax) ? g.Ng : key;
           d.gindex[i] = key;
           atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, 1);
           if (key == g.Ng)
@@ -550,6 +551,7 @@ row_mma_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
     __syncwarp();
 
   const double xmin = lim[4], ymin = lim[2], zmin = lim[0];
+  const double xmax = lim[5], ymax = lim[3], zmax = lim[1]; // in registers: the key tests run per particle
   const double rdx = rc.rd[2], rdy = rc.rd[1], rdz = rc.rd[0];
   const double dx = rc.del[2], dy = rc.del[1], dz = rc.del[0];
   // cell-centre ("integer") and cell-edge ("half") grid points of this row, pic/engine/velocity.hpp:304-315
@@ -680,9 +682,9 @@ row_mma_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
         const int iz1 = digitize(z1, zmin, rdz);
         if (FUSED) {
           int key = iz1 * g.fsz + iy1 * g.fsy + ix1;
-          key     = (x1 < xmin || x1 >= lim[5]) ? g.Ng : key;
-          key     = (y1 < ymin || y1 >= lim[3]) ? g.Ng : key;
-          key     = (z1 < zmin || z1 >= lim[1]) ? g.Ng : key;
+          key     = (x1 < xmin || x1 >= xmax) ? g.Ng : key;
+          key     = (y1 < ymin || y1 >= ymax) ? g.Ng : key;
+          key     = (z1 < zmin || z1 >= zmax) ? g.Ng : key;
           d.gindex[i] = key;
           atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, 1);
           if (key == g.Ng)
