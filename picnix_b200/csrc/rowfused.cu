@@ -369,20 +369,30 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
       __syncwarp();
 
       // ---------------- phase 2: one staged particle per half-warp ----------------
+      // Which passes can take the register-only fast path is decided here once per batch, without
+      // shared-memory loads or votes inside the loop: particle j continues the run of its half-warp
+      // iff it has the majority window and the same info word as its predecessor j-2 (for j < 2: as
+      // the run carried over from the previous batch).  Bit j of `chg` is set otherwise.
+      unsigned chg;
+      {
+        int pred = __shfl_up_sync(FULL, inf, 2);
+        const int carried = __shfl_sync(FULL, curinfo, (lane & 1) << 4);
+        if (lane < 2)
+          pred = carried;
+        const bool runs_on = ((inf >> 8) & 0xf) == 0xf && inf == pred;
+        chg                = __ballot_sync(FULL, !runs_on);
+      }
       const int npass = (n + 1) >> 1;
-      int       pinf_next = ws->info[half];
       for (int k = 0; k < npass; k++) {
-        const int     j    = 2 * k + half;
-        const int     pinf = pinf_next;
-        const double* rec  = ws->stg + j * REC;
-        // the info word of the next pass is requested now, so the vote below never waits for it
-        pinf_next = ws->info[(j + 2) & 31];
+        const int     j   = 2 * k + half;
+        const double* rec = ws->stg + j * REC;
 
         // common case: both particles belong to the cells already being accumulated
-        if (__all_sync(FULL, pinf == curinfo)) {
+        if (((chg >> (2 * k)) & 3u) == 0u) {
           accumulate(acc, rec, a, b);
           continue;
         }
+        const int pinf = ws->info[j];
 
         const bool valid = (pinf >> 11) & 1;
         const int  jx    = pinf & 0xff;
