@@ -94,6 +94,12 @@ __device__ __forceinline__ void cp_async_i32(int* smem, const int* gmem)
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
 }
+// 16-byte variant (L2 only): the field tile goes global -> shared without passing through registers
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem)
+{
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit_wait()
 {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");

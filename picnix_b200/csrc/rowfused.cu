@@ -167,17 +167,19 @@ row_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
       const int col = e - row * (FROW / 2);
       const int tz  = row / FY;
       const int ty  = row - tz * FY;
-      const double2 v = __ldg(reinterpret_cast<const double2*>(
-                                  uf + ((int64_t)((gz + tz) * My + (gy + ty)) * Mx + gx) * 6) + col);
-      reinterpret_cast<double2*>(ftile + tz * FSLAB + ty * FROW)[col] = v;
+      // asynchronous copy: the tile arrives while the current tile is being cleared below
+      cp_async_16(reinterpret_cast<double2*>(ftile + tz * FSLAB + ty * FROW) + col,
+                  reinterpret_cast<const double2*>(uf + ((int64_t)((gz + tz) * My + (gy + ty)) * Mx + gx) * 6) + col);
     }
   }
   for (int i = lane; i < TILE; i += 32)
     ws->tile[i] = 0.0;
-  if (FUSED)
+  if (FUSED) {
+    cp_async_commit_wait();
     __syncthreads();
-  else
+  } else {
     __syncwarp();
+  }
 
   const double xmin = lim[4], ymin = lim[2], zmin = lim[0];
   const double xmax = lim[5], ymax = lim[3], zmax = lim[1]; // in registers: the key tests run per particle
