@@ -615,15 +615,20 @@ int launch_halo_begin(picnix_arena* a, int mode)
       a->kernel_launches++;
       a->leave_list_valid = false; // appended migrants are not on the list
     }
-    // exact send sizes must be known to the host before the transfer (like MPI_Get_count)
-    for (auto& p : a->peers) {
-      int count = 0;
-      PICNIX_CUDA(a, cudaMemcpyAsync(&count, p.d_psend_count, sizeof(int), cudaMemcpyDeviceToHost,
-                                     a->stream));
+    // exact send sizes must be known to the host before the transfer (like MPI_Get_count): all
+    // peers' counters come back with ONE synchronisation
+    if (!a->peers.empty()) {
+      std::vector<int> counts(a->peers.size(), 0);
+      for (size_t i = 0; i < a->peers.size(); i++)
+        PICNIX_CUDA(a, cudaMemcpyAsync(&counts[i], a->peers[i].d_psend_count, sizeof(int),
+                                       cudaMemcpyDeviceToHost, a->stream));
       PICNIX_CUDA(a, cudaStreamSynchronize(a->stream));
-      count         = (int)std::min<int64_t>(count, p.pcap_send);
-      p.psend_bytes = (int64_t)count * 8 * sizeof(double);
-      p.precv_bytes = 0;
+      for (size_t i = 0; i < a->peers.size(); i++) {
+        PeerPlan& p   = a->peers[i];
+        int64_t count = std::min<int64_t>(counts[i], p.pcap_send);
+        p.psend_bytes = count * 8 * (int64_t)sizeof(double);
+        p.precv_bytes = 0;
+      }
     }
     break;
   }

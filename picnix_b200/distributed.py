@@ -100,8 +100,9 @@ class Transport:
             scount = [torch.tensor([b[1]], dtype=torch.int64, device=self.device) for b in bufs]
             rcount = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in bufs]
             self._exchange([(p, s, r) for p, s, r in zip(self.peers, scount, rcount)])
-            for i, r in enumerate(rcount):
-                self.sim.set_recv_bytes(mode, i, int(r.item()))
+            counts = torch.cat(rcount).cpu().tolist()  # one synchronisation for all peers
+            for i, nbytes in enumerate(counts):
+                self.sim.set_recv_bytes(mode, i, int(nbytes))
         pairs = []
         for i, peer in enumerate(self.peers):
             sp, sb, rp, rb = self.sim.comm_buffer(mode, i)
