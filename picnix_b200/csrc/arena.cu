@@ -478,6 +478,12 @@ int picnix_cuda_arena_destroy(picnix_arena_t* a)
     cudaFree(a->d_scan_tmp);
   if (a->h_stage)
     cudaFreeHost(a->h_stage);
+  if (a->h_mig)
+    cudaFreeHost(a->h_mig);
+  if (a->h_bounds)
+    cudaFreeHost(a->h_bounds);
+  if (a->mig_event)
+    cudaEventDestroy(a->mig_event);
   for (auto& p : a->peers) {
     dev_free(p.d_send_desc);
     dev_free(p.d_recv_desc);
@@ -490,6 +496,7 @@ int picnix_cuda_arena_destroy(picnix_arena_t* a)
     dev_free(p.d_psend);
     dev_free(p.d_precv);
     dev_free(p.d_psend_count);
+    dev_free(p.d_rcount);
   }
   if (a->own_stream && a->stream)
     cudaStreamDestroy(a->stream);

@@ -102,6 +102,11 @@ struct PeerPlan {
   int*                 d_psend_count = nullptr; // device counter
   int64_t              pcap_send = 0, pcap_recv = 0;
   int64_t              psend_bytes = 0, precv_bytes = 0;
+  // lagged-count migration protocol (option "async_migration"): records sent / received in the
+  // previous step (-1: unknown) and the message bounds both sides derive from them
+  int64_t              last_sent = -1, last_recv = -1;
+  int64_t              send_bound = 0, recv_bound = 0;
+  int*                 d_rcount = nullptr; // device copy of the count found in the received header
 };
 
 } // namespace picnix
@@ -147,6 +152,12 @@ struct picnix_arena {
   bool                   pindex_valid = false;  // pindex matches the particle order (after a sort)
   bool                   leave_list_valid = false; // DevPtrs::leave_idx describes the current keys
   bool                   lazy_sort    = true;   // option "lazy_sort": allow index-only sorts (see sort.cu)
+  bool                   async_migration = false; // option "async_migration": no host sync in the particle exchange
+  bool                   mig_async_step  = false; // the exchange in flight uses the lagged-count protocol
+  int*                   h_mig      = nullptr;    // pinned [npeer][2]: sent / received counts of the last step
+  int64_t*               h_bounds   = nullptr;    // pinned [npeer]: per-step send bounds (device caps)
+  cudaEvent_t            mig_event  = nullptr;
+  bool                   mig_pending = false;     // h_mig will hold the counts of the last step after mig_event
   bool                   perm_pending = false;  // xu is NOT yet in pindex order: DevPtrs::perm holds the order
   bool                   force_generic = false; // testing: bypass the tiled kernels
   bool                   deposit_mma   = false; // row kernel variant: deposit through the FP64 MMA unit

@@ -36,6 +36,10 @@ int picnix_cuda_set_option(picnix_arena_t* a, const char* key, int64_t value)
     a->lazy_sort = value != 0;
     return status;
   }
+  if (std::string(key) == "async_migration") {
+    a->async_migration = value != 0;
+    return PICNIX_OK;
+  }
   if (std::string(key) == "deposit_mma") {
     a->deposit_mma = value != 0;
     return PICNIX_OK;

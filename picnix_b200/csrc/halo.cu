@@ -497,6 +497,8 @@ int build_comm_plan(picnix_arena* a)
 
 // Particle staging buffers depend on the particle capacity, so they are sized lazily:
 // a fraction of the largest local population per peer (records of 64 B).
+constexpr int64_t MIG_MIN_BOUND = 16384; // records; smallest message bound of the lagged-count protocol
+
 static int ensure_particle_staging(picnix_arena* a)
 {
   if (a->peers.empty() || a->d_psend_ptrs != nullptr)
@@ -505,15 +507,18 @@ static int ensure_particle_staging(picnix_arena* a)
   for (int s = 0; s < a->nseg; s++)
     total_cap += a->seg_cap[s];
   // everything that can leave through one face in a step is far below 1/4 of the population
-  int64_t cap = std::max<int64_t>(4096, total_cap / 4);
+  int64_t cap = std::max<int64_t>(MIG_MIN_BOUND, total_cap / 4);
   std::vector<double*> ptrs;
   std::vector<int*>    cnts;
   std::vector<int64_t> caps;
   for (auto& p : a->peers) {
     p.pcap_send = cap;
     p.pcap_recv = cap;
-    PICNIX_CUDA(a, cudaMalloc((void**)&p.d_psend, cap * 8 * sizeof(double)));
-    PICNIX_CUDA(a, cudaMalloc((void**)&p.d_precv, cap * 8 * sizeof(double)));
+    // + 1 record: the lagged-count protocol appends a 64-byte header (the record count)
+    PICNIX_CUDA(a, cudaMalloc((void**)&p.d_psend, (cap + 1) * 8 * sizeof(double)));
+    PICNIX_CUDA(a, cudaMalloc((void**)&p.d_precv, (cap + 1) * 8 * sizeof(double)));
+    PICNIX_CUDA(a, cudaMalloc((void**)&p.d_rcount, sizeof(int)));
+    PICNIX_CUDA(a, cudaMemset(p.d_rcount, 0, sizeof(int)));
     ptrs.push_back(p.d_psend);
     cnts.push_back(p.d_psend_count);
     caps.push_back(cap);
@@ -525,7 +530,79 @@ static int ensure_particle_staging(picnix_arena* a)
     return status;
   if ((status = upload_vector(a, &a->d_psend_caps, caps)) != PICNIX_OK)
     return status;
+  PICNIX_CUDA(a, cudaMallocHost((void**)&a->h_mig, a->peers.size() * 2 * sizeof(int)));
+  PICNIX_CUDA(a, cudaMallocHost((void**)&a->h_bounds, a->peers.size() * sizeof(int64_t)));
+  PICNIX_CUDA(a, cudaEventCreateWithFlags(&a->mig_event, cudaEventDisableTiming));
   return PICNIX_OK;
+}
+
+// ---- lagged-count migration protocol -------------------------------------------------------------
+// The synchronous protocol reads the number of records per peer back to the host in the middle of
+// the step (like MPI_Get_count, nix/chunk.cpp:329-345); that synchronisation exposes the launch
+// latency of everything enqueued after it.  Here both sides size the message from the count of the
+// PREVIOUS step (sender: what it sent, receiver: what it found in the header -- the same number),
+// bound = max(16384, 2 x previous), and the actual count travels in a 64-byte header behind the
+// records.  Counts come back to the host one step late, from pinned memory, without a stall.  A step
+// that exceeds its bound raises the send-overflow flag (PICNIX_ERR_OVERFLOW at the next
+// synchronize) instead of losing particles silently.
+__global__ void migration_header_kernel(double** psend, int** counts, const int64_t* bounds, int npeer)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npeer)
+    psend[i][bounds[i] * 8] = (double)*counts[i];
+}
+
+__global__ void __launch_bounds__(HALO_THREADS)
+unpack_particle_bounded_kernel(Geom g, DevPtrs d, const double* __restrict__ recv, int64_t bound,
+                               int* rcount, int chunk_begin)
+{
+  const int count = (int)recv[bound * 8];
+  const int nrec  = count < bound ? count : (int)bound;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *rcount = count;
+    if (count > bound)
+      atomicExch(d.errflag + 1, 1);
+  }
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrec; r += gridDim.x * blockDim.x) {
+    const double* in = recv + (int64_t)r * 8;
+    double        p[NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++)
+      p[k] = in[k];
+    double tagbits = in[7];
+    int2   tag     = *reinterpret_cast<int2*>(&tagbits);
+    int    chunk   = tag.x - chunk_begin;
+    if (chunk < 0 || chunk >= g.nchunk || tag.y < 0 || tag.y >= g.Ns) {
+      atomicExch(d.errflag + 2, 1);
+      continue;
+    }
+    append_particle(g, d, chunk, tag.y, p);
+  }
+}
+
+// The bound of a message is a function of the previous count ONLY (both sides must compute the same
+// number, and their buffer capacities differ): a buffer that is too small for it is grown.
+static int ensure_peer_capacity(picnix_arena* a, size_t i, int64_t need)
+{
+  PeerPlan& p = a->peers[i];
+  if (need <= p.pcap_send)
+    return PICNIX_OK;
+  PICNIX_CUDA(a, cudaStreamSynchronize(a->stream));
+  cudaFree(p.d_psend);
+  cudaFree(p.d_precv);
+  PICNIX_CUDA(a, cudaMalloc((void**)&p.d_psend, (need + 1) * 8 * sizeof(double)));
+  PICNIX_CUDA(a, cudaMalloc((void**)&p.d_precv, (need + 1) * 8 * sizeof(double)));
+  p.pcap_send = p.pcap_recv = need;
+  PICNIX_CUDA(a, cudaMemcpy(a->d_psend_ptrs + i, &p.d_psend, sizeof(double*), cudaMemcpyHostToDevice));
+  return PICNIX_OK;
+}
+
+static bool migration_history_ready(const picnix_arena* a)
+{
+  for (const auto& p : a->peers)
+    if (p.last_sent < 0 || p.last_recv < 0)
+      return false;
+  return !a->peers.empty();
 }
 
 int launch_halo_begin(picnix_arena* a, int mode)
@@ -596,6 +673,32 @@ int launch_halo_begin(picnix_arena* a, int mode)
       return status;
     for (auto& p : a->peers)
       PICNIX_CUDA(a, cudaMemsetAsync(p.d_psend_count, 0, sizeof(int), a->stream));
+    // lagged-count protocol: bounds from the counts of the previous step (already on the host)
+    if (a->mig_pending) {
+      PICNIX_CUDA(a, cudaEventSynchronize(a->mig_event)); // recorded a step ago: no stall in steady state
+      for (size_t i = 0; i < a->peers.size(); i++) {
+        a->peers[i].last_sent = a->h_mig[2 * i + 0];
+        a->peers[i].last_recv = a->h_mig[2 * i + 1];
+      }
+      a->mig_pending = false;
+    }
+    a->mig_async_step = a->async_migration && migration_history_ready(a);
+    for (size_t i = 0; i < a->peers.size(); i++) {
+      PeerPlan& p = a->peers[i];
+      if (a->mig_async_step) {
+        p.send_bound = std::max<int64_t>(MIG_MIN_BOUND, 2 * p.last_sent);
+        p.recv_bound = std::max<int64_t>(MIG_MIN_BOUND, 2 * p.last_recv);
+        int gstatus  = ensure_peer_capacity(a, i, std::max(p.send_bound, p.recv_bound));
+        if (gstatus != PICNIX_OK)
+          return gstatus;
+        a->h_bounds[i] = p.send_bound;
+      } else {
+        a->h_bounds[i] = p.pcap_send;
+      }
+    }
+    if (!a->peers.empty())
+      PICNIX_CUDA(a, cudaMemcpyAsync(a->d_psend_caps, a->h_bounds, a->peers.size() * sizeof(int64_t),
+                                     cudaMemcpyHostToDevice, a->stream));
     int maxcap = 0;
     for (int s = 0; s < a->nseg; s++)
       maxcap = std::max(maxcap, a->seg_cap[s]);
@@ -615,9 +718,21 @@ int launch_halo_begin(picnix_arena* a, int mode)
       a->kernel_launches++;
       a->leave_list_valid = false; // appended migrants are not on the list
     }
-    // exact send sizes must be known to the host before the transfer (like MPI_Get_count): all
-    // peers' counters come back with ONE synchronisation
-    if (!a->peers.empty()) {
+    if (a->mig_async_step) {
+      // header behind the records, count back to the host for the NEXT step; no synchronisation
+      const int npeer = (int)a->peers.size();
+      migration_header_kernel<<<1, 32, 0, a->stream>>>(a->d_psend_ptrs, a->d_psend_cnts, a->d_psend_caps, npeer);
+      a->kernel_launches++;
+      for (int i = 0; i < npeer; i++) {
+        PeerPlan& p = a->peers[i];
+        PICNIX_CUDA(a, cudaMemcpyAsync(a->h_mig + 2 * i, p.d_psend_count, sizeof(int), cudaMemcpyDeviceToHost,
+                                       a->stream));
+        p.psend_bytes = (p.send_bound + 1) * 8 * (int64_t)sizeof(double);
+        p.precv_bytes = (p.recv_bound + 1) * 8 * (int64_t)sizeof(double);
+      }
+    } else if (!a->peers.empty()) {
+      // exact send sizes must be known to the host before the transfer (like MPI_Get_count): all
+      // peers' counters come back with ONE synchronisation
       std::vector<int> counts(a->peers.size(), 0);
       for (size_t i = 0; i < a->peers.size(); i++)
         PICNIX_CUDA(a, cudaMemcpyAsync(&counts[i], a->peers[i].d_psend_count, sizeof(int),
@@ -628,6 +743,7 @@ int launch_halo_begin(picnix_arena* a, int mode)
         int64_t count = std::min<int64_t>(counts[i], p.pcap_send);
         p.psend_bytes = count * 8 * (int64_t)sizeof(double);
         p.precv_bytes = 0;
+        p.last_sent   = count;
       }
     }
     break;
@@ -673,12 +789,26 @@ int launch_halo_end(picnix_arena* a, int mode)
     }
     break;
   case PICNIX_BOUNDARY_PARTICLE: {
-    for (auto& p : a->peers) {
-      int nrec = (int)(p.precv_bytes / (8 * sizeof(double)));
-      if (nrec > 0) {
-        unpack_particle_kernel<<<(nrec + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, 0,
-                                 a->stream>>>(g, a->d, p.d_precv, nrec, a->chunk_begin);
+    if (a->mig_async_step) {
+      for (size_t i = 0; i < a->peers.size(); i++) {
+        PeerPlan& p = a->peers[i];
+        unpack_particle_bounded_kernel<<<148 * 2, HALO_THREADS, 0, a->stream>>>(g, a->d, p.d_precv, p.recv_bound,
+                                                                               p.d_rcount, a->chunk_begin);
         a->kernel_launches++;
+        PICNIX_CUDA(a, cudaMemcpyAsync(a->h_mig + 2 * i + 1, p.d_rcount, sizeof(int), cudaMemcpyDeviceToHost,
+                                       a->stream));
+      }
+      PICNIX_CUDA(a, cudaEventRecord(a->mig_event, a->stream));
+      a->mig_pending = true;
+    } else {
+      for (auto& p : a->peers) {
+        int nrec = (int)(p.precv_bytes / (8 * sizeof(double)));
+        if (nrec > 0) {
+          unpack_particle_kernel<<<(nrec + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, 0,
+                                   a->stream>>>(g, a->d, p.d_precv, nrec, a->chunk_begin);
+          a->kernel_launches++;
+        }
+        p.last_recv = nrec;
       }
     }
     // post_unpack ends with sort() for every species (nix/xtensor_halo3d.hpp:495-497)
@@ -745,7 +875,7 @@ int picnix_cuda_set_recv_bytes(picnix_arena_t* a, int32_t mode, int32_t peer_ind
       mode != PICNIX_BOUNDARY_PARTICLE)
     return PICNIX_ERR_INVALID;
   PeerPlan& p = a->peers[peer_index];
-  if (recv_bytes < 0 || recv_bytes > p.pcap_recv * 8 * (int64_t)sizeof(double))
+  if (recv_bytes < 0 || recv_bytes > (p.pcap_recv + 1) * 8 * (int64_t)sizeof(double))
     return fail(a, PICNIX_ERR_OVERFLOW, "particle receive buffer too small");
   p.precv_bytes = recv_bytes;
   return PICNIX_OK;

@@ -94,15 +94,17 @@ class Transport:
         import torch
 
         if mode == MODE_PARTICLE:
-            # variable size: first the byte counts (the reference sizes its receive with
-            # MPI_Iprobe + MPI_Get_count, nix/chunk.cpp:329-345), then the payload
             bufs = [self.sim.comm_buffer(mode, i) for i in range(len(self.peers))]
-            scount = [torch.tensor([b[1]], dtype=torch.int64, device=self.device) for b in bufs]
-            rcount = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in bufs]
-            self._exchange([(p, s, r) for p, s, r in zip(self.peers, scount, rcount)])
-            counts = torch.cat(rcount).cpu().tolist()  # one synchronisation for all peers
-            for i, nbytes in enumerate(counts):
-                self.sim.set_recv_bytes(mode, i, int(nbytes))
+            if any(b[3] == 0 for b in bufs):
+                # synchronous protocol, variable size: first the byte counts (the reference sizes its
+                # receive with MPI_Iprobe + MPI_Get_count, nix/chunk.cpp:329-345), then the payload.
+                # With the lagged-count protocol (option async_migration) both sizes are already known.
+                scount = [torch.tensor([b[1]], dtype=torch.int64, device=self.device) for b in bufs]
+                rcount = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in bufs]
+                self._exchange([(p, s, r) for p, s, r in zip(self.peers, scount, rcount)])
+                counts = torch.cat(rcount).cpu().tolist()  # one synchronisation for all peers
+                for i, nbytes in enumerate(counts):
+                    self.sim.set_recv_bytes(mode, i, int(nbytes))
         pairs = []
         for i, peer in enumerate(self.peers):
             sp, sb, rp, rb = self.sim.comm_buffer(mode, i)
@@ -181,9 +183,13 @@ def rebalance_in_process(sims, new_boundary, make_sim):
 class DistributedSim(CudaSim):
     """CudaSim whose chunk ids are split over `world` ranks like the reference's MPI ranks."""
 
-    def __init__(self, ndims, cdims, Ns, cc, rank=0, world=1, block_layout=None, boundary=None, **kw):
+    def __init__(self, ndims, cdims, Ns, cc, rank=0, world=1, block_layout=None, boundary=None,
+                 async_migration=True, **kw):
         super().__init__(ndims, cdims, Ns, cc, nrank=world, rank=rank, boundary=boundary, **kw)
         self.rank, self.world = rank, world
+        if world > 1 and async_migration:
+            # particle exchange without a host synchronisation in the middle of the step (halo.cu)
+            self.set_option("async_migration", 1)
         self.transport = Transport(self, world, device_buffers=True)
 
     def exchange(self, mode):

@@ -92,9 +92,10 @@ def step_all(sims, dt):
         s.boundary_end(MODE_EMF)
 
 
+@pytest.mark.parametrize("async_migration", [0, 1])
 @pytest.mark.parametrize("ndims,cdims,nrank", [((1, 32, 32), (1, 4, 4), 3), ((16, 16, 16), (2, 2, 2), 2),
                                                ((16, 32, 16), (2, 4, 2), 4)])
-def test_ranks_on_one_device_equal_single_arena(ndims, cdims, nrank):
+def test_ranks_on_one_device_equal_single_arena(ndims, cdims, nrank, async_migration):
     from picnix_b200 import CudaSim
 
     species, ppc, cc, B0, dt, nstep = problems.THERMAL_SPECIES, (8, 8), 10.0, (5.0, 0.0, 0.0), 0.05, 12
@@ -110,6 +111,7 @@ def test_ranks_on_one_device_equal_single_arena(ndims, cdims, nrank):
     sims = [CudaSim(ndims, cdims, nrank=nrank, rank=r, boundary=boundary, **kw) for r in range(nrank)]
     for s in sims:
         assert s.chunk_id_begin == boundary[s.cfg.rank] and s.nchunk == boundary[s.cfg.rank + 1] - boundary[s.cfg.rank]
+        s.set_option("async_migration", async_migration)  # lagged-count particle exchange (no host sync)
         fill(s, ndims, cdims, species, ppc, B0)
     exchange_all(sims, MODE_EMF)
 
