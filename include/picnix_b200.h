@@ -112,7 +112,11 @@ const char* picnix_cuda_last_error(const picnix_arena_t* arena);
  *   "lazy_sort"     = 0  the counting sort always moves the particles (default 1: when the tiled
  *                        fused kernel will consume the result only the permutation is written and
  *                        the reordering rides on the next push; results are identical)
- *   "deposit_mma"   = 1  FP64-MMA formulation of the deposit (slower; kept as measured evidence) */
+ *   "deposit_mma"   = 1  FP64-MMA formulation of the deposit (slower; kept as measured evidence)
+ *   "async_migration" = 1  multi-rank particle exchange without a host synchronisation: message
+ *                        sizes follow from the previous step's counts (both sides compute the same
+ *                        bound, get_comm_buffer returns send AND receive sizes, set_recv_bytes is not
+ *                        needed), the actual count travels in a 64-byte header behind the records */
 int picnix_cuda_set_option(picnix_arena_t* arena, const char* key, int64_t value);
 
 /* use an existing CUDA stream (cudaStream_t as void*); default is a stream the arena owns */
