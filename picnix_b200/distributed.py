@@ -11,6 +11,7 @@ send/recv of the buffers the CUDA library packed, and the final timing reduction
 `Transport` is backend agnostic (device buffers for the CUDA arena, host buffers for the CPU oracle
 that the gloo tests use), so the message planning is covered by world_size-2 CPU tests.
 """
+import os
 import time
 
 import numpy as np
@@ -187,6 +188,8 @@ class DistributedSim(CudaSim):
                  async_migration=True, **kw):
         super().__init__(ndims, cdims, Ns, cc, nrank=world, rank=rank, boundary=boundary, **kw)
         self.rank, self.world = rank, world
+        if os.environ.get("PICNIX_ASYNC_MIGRATION", "1") == "0":
+            async_migration = False  # escape hatch: the synchronous count exchange of the first version
         if world > 1 and async_migration:
             # particle exchange without a host synchronisation in the middle of the step (halo.cu)
             self.set_option("async_migration", 1)
