@@ -44,9 +44,9 @@ typedef struct {
   int      rank;
   int      nsend, nrecv;
   int     *send_chunk, *send_dir, *recv_chunk, *recv_dir; /* canonical order */
-  int64_t *send_off[2], *recv_off[2];                     /* element offsets per mode (EMF, CUR) */
-  int64_t  send_elems[2], recv_elems[2];
-  double  *send[2], *recv[2];
+  int64_t *send_off[3], *recv_off[3];                     /* element offsets per mode (EMF, CUR, MOM) */
+  int64_t  send_elems[3], recv_elems[3];
+  double  *send[3], *recv[3];
   double  *psend, *precv;
   int64_t  psend_cap, precv_cap, psend_bytes, precv_bytes;
 } peer_t;
@@ -507,8 +507,8 @@ static void build_peers(orc_sim_t* s)
     p->send_dir   = (int*)malloc(sizeof(int) * (ns + 1));
     p->recv_chunk = (int*)malloc(sizeof(int) * (nrv + 1));
     p->recv_dir   = (int*)malloc(sizeof(int) * (nrv + 1));
-    for (int mode = 0; mode < 2; mode++) {
-      int ncomp         = mode == 0 ? 6 : 4;
+    for (int mode = 0; mode < 3; mode++) {
+      int ncomp         = mode == 0 ? 6 : (mode == 1 ? 4 : s->cfg.Ns * 14);
       p->send_off[mode] = (int64_t*)malloc(sizeof(int64_t) * (ns + 1));
       p->recv_off[mode] = (int64_t*)malloc(sizeof(int64_t) * (nrv + 1));
       int64_t off       = 0;
@@ -663,7 +663,7 @@ void orc_destroy(orc_sim_t* s)
     free(p->send_dir);
     free(p->recv_chunk);
     free(p->recv_dir);
-    for (int m = 0; m < 2; m++) {
+    for (int m = 0; m < 3; m++) {
       free(p->send_off[m]);
       free(p->recv_off[m]);
       free(p->send[m]);
@@ -1645,12 +1645,21 @@ static void region_unpack(const orc_sim_t* s, double* dst, const int dlo[3], con
       }
 }
 
-static double* chunk_field(chunk_t* c, int mode) { return mode == MODE_EMF ? c->uf : c->uj; }
+/* EMF copies interior margin -> ghost; CUR and MOM add ghost -> interior margin
+ * (XtensorHaloField3D / Current3D / Moment3D, nix/xtensor_halo3d.hpp:18-185) */
+static double* chunk_field(chunk_t* c, int mode)
+{
+  return mode == MODE_EMF ? c->uf : (mode == MODE_CUR ? c->uj : c->um);
+}
+static int mode_ncomp(const orc_sim_t* s, int mode)
+{
+  return mode == MODE_EMF ? 6 : (mode == MODE_CUR ? 4 : s->cfg.Ns * 14);
+}
 
 /* field / current: pack the messages for remote neighbours */
 static void field_begin(orc_sim_t* s, int mode)
 {
-  const int ncomp = mode == MODE_EMF ? 6 : 4;
+  const int ncomp = mode_ncomp(s, mode);
   for (int pi = 0; pi < s->npeer; pi++) {
     peer_t* p = &s->peers[pi];
     for (int m = 0; m < p->nsend; m++) {
@@ -1678,7 +1687,8 @@ static int find_recv_msg(const peer_t* p, int ic, int d)
 /* unpack in the reference's order: directions ascending (nix/chunk.hpp:437-455) */
 static void field_end(orc_sim_t* s, int mode)
 {
-  const int ncomp = mode == MODE_EMF ? 6 : 4;
+  const int ncomp = mode_ncomp(s, mode);
+  const int add   = mode != MODE_EMF;
 #pragma omp parallel for schedule(dynamic) num_threads(s->nthread)
   for (int ic = 0; ic < s->nchunk; ic++) {
     chunk_t* c = &s->chunks[ic];
@@ -1696,12 +1706,11 @@ static void field_end(orc_sim_t* s, int mode)
       }
       if (c->nbrank[d] == s->cfg.rank) {
         chunk_t* nbc = &s->chunks[c->nbid[d] - s->chunk_begin];
-        region_apply(s, chunk_field(c, mode), dlo, chunk_field(nbc, mode), slo, len, ncomp, mode == MODE_CUR);
+        region_apply(s, chunk_field(c, mode), dlo, chunk_field(nbc, mode), slo, len, ncomp, add);
       } else {
         peer_t* p = &s->peers[s->peer_of_rank[c->nbrank[d]]];
         int     m = find_recv_msg(p, ic, d);
-        region_unpack(s, chunk_field(c, mode), dlo, len, p->recv[mode] + p->recv_off[mode][m], ncomp,
-                      mode == MODE_CUR);
+        region_unpack(s, chunk_field(c, mode), dlo, len, p->recv[mode] + p->recv_off[mode][m], ncomp, add);
       }
     }
   }
@@ -1909,7 +1918,7 @@ static void particle_end(orc_sim_t* s)
 
 void orc_boundary_begin(orc_sim_t* s, int mode)
 {
-  if (mode == MODE_EMF || mode == MODE_CUR)
+  if (mode == MODE_EMF || mode == MODE_CUR || mode == MODE_MOM)
     field_begin(s, mode);
   else if (mode == MODE_PARTICLE)
     particle_begin(s);
@@ -1917,7 +1926,7 @@ void orc_boundary_begin(orc_sim_t* s, int mode)
 
 void orc_boundary_end(orc_sim_t* s, int mode)
 {
-  if (mode == MODE_EMF || mode == MODE_CUR)
+  if (mode == MODE_EMF || mode == MODE_CUR || mode == MODE_MOM)
     field_end(s, mode);
   else if (mode == MODE_PARTICLE)
     particle_end(s);

@@ -55,10 +55,13 @@ def _worker(rank, world, port, case, outdir):
     distributed.exchange(sim, tr, distributed.MODE_EMF)
     for _ in range(nstep):
         distributed.step_phases(sim, tr, dt)
+    sim.deposit_moment()
+    distributed.exchange(sim, tr, distributed.MODE_MOM)
     out = {"begin": np.array(sim.chunk_id_begin), "nchunk": np.array(sim.nchunk), "peers": np.array(sim.peers())}
     for ic in range(sim.nchunk):
         out[f"uf_{ic}"] = sim.get_field(ic, 0)
         out[f"uj_{ic}"] = sim.get_field(ic, 1)
+        out[f"um_{ic}"] = sim.get_field(ic, 3)
         for isp in range(sim.Ns):
             out[f"xu_{ic}_{isp}"] = sim.get_particles(ic, isp)
             out[f"pindex_{ic}_{isp}"] = sim.get_pindex(ic, isp)
@@ -83,6 +86,8 @@ def test_two_ranks_equal_one_rank(case, tmp_path):
     _setup(single, case, 0)
     single.finalize_setup()
     single.step(dt, nstep)
+    single.deposit_moment()
+    single.exchange(2)
 
     seen = 0
     for rank in range(world):
@@ -93,6 +98,7 @@ def test_two_ranks_equal_one_rank(case, tmp_path):
             gid = begin + ic
             assert np.array_equal(g[f"uf_{ic}"], single.get_field(gid, 0)), (case, "uf", gid)
             assert np.array_equal(g[f"uj_{ic}"], single.get_field(gid, 1)), (case, "uj", gid)
+            assert np.array_equal(g[f"um_{ic}"], single.get_field(gid, 3)), (case, "um", gid)
             for isp in range(single.Ns):
                 assert np.array_equal(g[f"pindex_{ic}_{isp}"], single.get_pindex(gid, isp))
                 a, b = g[f"xu_{ic}_{isp}"], single.get_particles(gid, isp)

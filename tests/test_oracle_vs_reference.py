@@ -154,6 +154,11 @@ def test_moments_and_energy(case, order):
         sim.deposit_moment()
     assert field_err(port, ref, 3) < 1e-13
     assert np.allclose(port.get_energy(), ref.get_energy(), rtol=1e-12, atol=1e-12)
+    # BoundaryMom exchange (nix/xtensor_halo3d.hpp:134-185): ghost -> neighbour, added into the margin
+    for sim in (ref, port):
+        sim.exchange(2)
+    assert field_err(port, ref, 3) < 1e-13
+    assert np.allclose(port.get_energy(), ref.get_energy(), rtol=1e-12, atol=1e-12)
 
 
 def test_rank_boundaries():
