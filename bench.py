@@ -54,8 +54,8 @@ BYTES_STEP_PER_CELL = 600
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)    # warm-up 10, time >= 50 steps
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=128, help="cells per GPU per dimension")
     ap.add_argument("--ppc", type=int, default=32, help="particles per cell per species")
@@ -64,6 +64,8 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-cells", type=int, default=64, help="cells per dimension of the CPU sample")
     ap.add_argument("--ref-steps", type=int, default=0, help="override steps of the reference arm")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed N>1 parity pre-check")
+    ap.add_argument("--parity-cells", type=int, default=32, help="cells per rank per dimension of the pre-check")
     return ap.parse_args()
 
 
@@ -150,6 +152,15 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm: the unmodified reference on the host cores
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """Every core this process may run on.  torch.distributed.run exports OMP_NUM_THREADS=1, which
+    would silently turn the reference arm into a one-thread run, so the count is passed explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(cells, ppc, steps, warmup):
     from oracle import ref_backend
     from picnix_b200 import problems
@@ -157,7 +168,7 @@ def run_reference(cells, ppc, steps, warmup):
     ndims = (cells, cells, cells)
     cdims = tuple(n // CHUNK for n in ndims)
     sim = ref_backend.RefSim(ndims, cdims, Ns=2, cc=CC, delh=DELH, order=ORDER, pusher=PUSHER, interp=INTERP,
-                             vector_mode=1, nthread=0)
+                             vector_mode=1, nthread=host_threads())
     problems.setup_uniform_plasma(sim, ndims, cdims, problems.THERMAL_SPECIES, (ppc, ppc), delh=DELH,
                                   B0=(BX, 0.0, 0.0), seed=1)
     npart = problems.total_particles(sim)
@@ -179,15 +190,22 @@ def run_reference(cells, ppc, steps, warmup):
 def reference_main(args, rank, world):
     if rank != 0:
         return
-    steps = args.ref_steps if args.ref_steps > 0 else max(3, min(args.steps, 10))
-    warmup = max(1, min(args.warmup, 2))
+    # the same --steps / --warmup as the B200 arm; every step is a bounded sample of the workload
+    # (ref_cells^3 cells of the same plasma: the CPU cost per particle does not depend on the box size)
+    steps = args.ref_steps if args.ref_steps > 0 else args.steps
+    warmup = args.warmup
     res = run_reference(args.ref_cells, args.ppc, steps, warmup)
+    cfg = workload_config(args, args.gpus)
+    cfg["workload"] += (f"; THIS ARM: CPU sample of {args.ref_cells}^3 cells of that plasma per step "
+                        f"({res['particles']} particles), {res['cores']} host threads")
+    cfg["sample_cells"] = args.ref_cells ** 3
+    cfg["sample_particles"] = res["particles"]
     line = {
         "impl": "reference",
         "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
                          "sample": res["sample"]},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -244,6 +262,75 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+def parity_precheck(args, rank, world, nstep=10):
+    """Untimed parity check of the very path the bench times (fused tiled push+deposit, lazy sort,
+    halos and migration -- over NCCL when world > 1) at the headline chunk shape: parity_cells^3
+    cells per rank in 16^3 chunks at the bench's ppc, `nstep` steps, every rank's chunks gathered on
+    rank 0 and compared there with the reference (oracle/_ref; the C restatement if it is absent)
+    run on the whole box.  pic/pic_application.cpp:219-292, nix/xtensor_halo3d.hpp:93-125."""
+    import torch
+    import torch.distributed as dist
+
+    from picnix_b200 import capi, problems
+    from picnix_b200.distributed import DistributedSim
+
+    lay = gpu_layout(world)
+    ndims = tuple(args.parity_cells * l for l in lay)
+    cdims = tuple(n // CHUNK for n in ndims)
+    kw = dict(Ns=2, cc=CC, delh=DELH, order=ORDER, pusher=PUSHER, interp=INTERP)
+    setup = dict(delh=DELH, B0=(BX, 0.0, 0.0), seed=5, perturb=0.01)
+    sim = DistributedSim(ndims, cdims, rank=rank, world=world, **kw)
+    sim.set_stream(torch.cuda.current_stream().cuda_stream)
+    problems.setup_uniform_plasma(sim, ndims, cdims, problems.THERMAL_SPECIES, (args.ppc, args.ppc),
+                                  chunk_id_begin=sim.chunk_id_begin, **setup)
+    for _ in range(nstep):
+        sim.step_phases(DELT)
+    sim.synchronize()
+    mine = {"begin": sim.chunk_id_begin,
+            "uf": [sim.get_field(ic, capi.FIELD_UF) for ic in range(sim.nchunk)],
+            "uj": [sim.get_field(ic, capi.FIELD_UJ) for ic in range(sim.nchunk)],
+            "np": sim.get_np_all(),
+            "pindex": [[sim.get_pindex(ic, isp) for isp in range(2)] for ic in range(sim.nchunk)]}
+    sim.close()
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+    else:
+        parts = [mine]
+    if rank != 0:
+        return None
+    from oracle import ref_backend
+
+    if ref_backend.available():
+        ref, name = ref_backend.RefSim(ndims, cdims, vector_mode=1, nthread=host_threads(), **kw), "reference (oracle/_ref)"
+    else:
+        from oracle import port_backend
+
+        ref, name = port_backend.PortSim(ndims, cdims, **kw), "C restatement (oracle/libpicnix_oracle.so)"
+    problems.setup_uniform_plasma(ref, ndims, cdims, problems.THERMAL_SPECIES, (args.ppc, args.ppc), **setup)
+    ref.step(DELT, nstep)
+    err_f = err_j = 0.0
+    counts = True
+    nchunk = 0
+    for part in parts:
+        for ic in range(len(part["uf"])):
+            gid = part["begin"] + ic
+            nchunk += 1
+            for which, key in ((capi.FIELD_UF, "uf"), (capi.FIELD_UJ, "uj")):
+                b = ref.get_field(gid, which)
+                e = float(np.max(np.abs(part[key][ic] - b)) / max(np.max(np.abs(b)), 1e-300))
+                if key == "uf":
+                    err_f = max(err_f, e)
+                else:
+                    err_j = max(err_j, e)
+            for isp in range(2):
+                counts = counts and int(part["np"][ic, isp]) == ref.get_np(gid, isp)
+                counts = counts and bool(np.array_equal(part["pindex"][ic][isp], ref.get_pindex(gid, isp)))
+    return {"oracle": name, "cells": list(ndims), "chunks": nchunk, "ppc": 2 * args.ppc, "steps": nstep,
+            "ranks": world, "max_rel_field_err": err_f, "max_rel_current_err": err_j, "counts_equal": counts,
+            "tolerance": 1e-10, "ok": bool(counts and err_f < 1e-10 and err_j < 1e-10)}
+
+
 def b200_main(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -263,11 +350,18 @@ def b200_main(args, rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_precheck(args, rank, world)
+        except Exception as exc:  # report, never hide: the line then says the check did not run
+            parity = {"ok": False, "error": f"{type(exc).__name__}: {exc}"}
+
     lay = gpu_layout(world)
     ndims = tuple(args.cells * l for l in lay)
     cdims = tuple(n // CHUNK for n in ndims)
     sim = DistributedSim(ndims, cdims, Ns=2, cc=CC, delh=DELH, order=ORDER, pusher=PUSHER, interp=INTERP,
-                         rank=rank, world=world, block_layout=lay)
+                         rank=rank, world=world)
     stream = torch.cuda.Stream()
     sim.set_stream(stream.cuda_stream)
     problems.setup_uniform_plasma(sim, ndims, cdims, problems.THERMAL_SPECIES, (args.ppc, args.ppc), delh=DELH,
@@ -387,6 +481,7 @@ def b200_main(args, rank, world):
             "particles_before_after": [np_total, np_after_total],
             "conservation": {"particles_conserved": np_total == np_after_total,
                              "max_chunk_abs_sum_divE_minus_rho": div_e_worst, "max_chunk_abs_sum_divB": div_b_worst},
+            "parity_check": parity,
             "clocks": clocks,
             "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0,
                                                 "d2h_bytes_per_step": 0, "note": "skipped (--no-e2e)"},

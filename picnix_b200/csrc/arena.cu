@@ -378,6 +378,8 @@ int picnix_cuda_arena_create(const picnix_config_t* cfg, const int32_t* boundary
   // tuning/testing override of the row-kernel variant (same as set_option("deposit_mma"))
   if (const char* env = std::getenv("PICNIX_DEPOSIT_MMA"))
     a->deposit_mma = std::atoi(env) != 0;
+  if (const char* env = std::getenv("PICNIX_ROW_KERNEL"))
+    a->row_version = std::atoi(env) == 1 ? 1 : 2;
   if (const char* env = std::getenv("PICNIX_LAZY_SORT"))
     a->lazy_sort = std::atoi(env) != 0;
   a->cfg = *cfg;
@@ -533,6 +535,10 @@ int picnix_cuda_synchronize(picnix_arena_t* a)
     return fail(a, PICNIX_ERR_OVERFLOW, "particle segment overflow (increase buffer_ratio)");
   if (flags[1] != 0)
     return fail(a, PICNIX_ERR_OVERFLOW, "particle migration send buffer overflow");
+  if (flags[2] != 0)
+    return fail(a, PICNIX_ERR_INVALID,
+                "received a particle for a chunk/species this rank does not own (decomposition or "
+                "message plan mismatch between ranks)");
   if (flags[3] != 0)
     return fail(a, PICNIX_ERR_OVERFLOW, "too many particles moved more than one cell in a step");
   return PICNIX_OK;

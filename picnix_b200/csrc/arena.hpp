@@ -161,6 +161,7 @@ struct picnix_arena {
   bool                   perm_pending = false;  // xu is NOT yet in pindex order: DevPtrs::perm holds the order
   bool                   force_generic = false; // testing: bypass the tiled kernels
   bool                   deposit_mma   = false; // row kernel variant: deposit through the FP64 MMA unit
+  int                    row_version   = 2;     // option "row_kernel": 2 = rowpush.cu, 1 = round-1 kernel (rowfused.cu)
   int64_t                kernel_launches = 0;
   int64_t                particle_pushes = 0;
   int64_t                np_total_hint   = 0; // sum of np at last host-visible count

@@ -40,6 +40,12 @@ int picnix_cuda_set_option(picnix_arena_t* a, const char* key, int64_t value)
     a->async_migration = value != 0;
     return PICNIX_OK;
   }
+  if (std::string(key) == "row_kernel") {
+    if (value != 1 && value != 2)
+      return fail(a, PICNIX_ERR_INVALID, "row_kernel must be 1 or 2");
+    a->row_version = (int)value;
+    return PICNIX_OK;
+  }
   if (std::string(key) == "deposit_mma") {
     a->deposit_mma = value != 0;
     return PICNIX_OK;

@@ -852,13 +852,23 @@ bool row_kernel_applies(const picnix_arena* a)
   return row_geometry_applies(a) && a->pindex_valid && !a->force_generic;
 }
 
+// rowpush.cu: the second formulation (merged species stream, cell-anchored interpolation, 2-D register
+// tiles); option "row_kernel" = 1 selects the round-1 kernel of this file instead
+bool row_push_applies(const picnix_arena* a);
+int  launch_deposit_rows_v2(picnix_arena* a, int c0, int cn, double delt);
+int  launch_row_fused_v2(picnix_arena* a, int c0, int cn, double delt);
+
 int launch_deposit_rows(picnix_arena* a, int c0, int cn, double delt)
 {
+  if (a->row_version >= 2 && !a->deposit_mma && row_push_applies(a))
+    return launch_deposit_rows_v2(a, c0, cn, delt);
   return launch_row_kernel<false>(a, c0, cn, delt);
 }
 
 int launch_row_fused(picnix_arena* a, int c0, int cn, double delt)
 {
+  if (a->row_version >= 2 && !a->deposit_mma && row_push_applies(a))
+    return launch_row_fused_v2(a, c0, cn, delt);
   return launch_row_kernel<true>(a, c0, cn, delt);
 }
 

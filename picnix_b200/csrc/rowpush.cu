@@ -1,0 +1,545 @@
+// -*- C++ -*-
+// Row-owner kernel (3-D, order 2), second formulation: see rowtile.cuh for the scheme.
+//   FUSED = true : phase 1 interpolates the fields, pushes momentum and position, writes the new
+//                  state and produces the cell key + histogram (K1 + K2 in one pass over the
+//                  particles: PicChunk::push_velocity + push_position + deposit_current,
+//                  pic/pic_chunk.cpp:491-523)
+//   FUSED = false: deposit only, old position from xv, new position from xu (PicChunk::deposit_current)
+// One block per (chunk, z, group of WARPS rows in y, x-segment of RX cells), one warp per row.  The
+// particles of a row segment are contiguous in every species' cell-sorted arrays,
+// [pindex[key0], pindex[key0+RX]); the warp walks them as ONE stream, cell by cell, all species of a cell
+// back to back, every cell starting at an even stream slot.
+#include "rowtile.cuh"
+
+namespace picnix
+{
+
+namespace
+{
+
+using namespace rowtile;
+
+// chunk-independent constants of the run, computed once on the host
+struct RowConst {
+  double rd[3];    // 1/dz, 1/dy, 1/dx
+  double del[3];   // dz, dy, dx
+  double ddt[3];   // dz/dt, dy/dt, dx/dt
+  double cc, rc, delt, cfl[3];
+};
+
+// Particles that moved more than one cell (never at a Courant-limited time step; the parity tests
+// provoke it with large steps) do not fit the 4-slot window.  They are appended to a list and
+// deposited by far_kernel with the generic stencil, which keeps that code out of the hot kernel.
+__device__ __forceinline__ void defer_far_mover(const DevPtrs& d, int chunk, double q, double x0,
+                                                double y0, double z0, double x1, double y1,
+                                                double z1)
+{
+  const int slot = atomicAdd(d.far_count, 1);
+  if (slot >= d.far_cap) {
+    atomicExch(d.errflag + 3, 1);
+    return;
+  }
+  double* r = d.far_rec + (int64_t)slot * 8;
+  r[0] = x0;
+  r[1] = y0;
+  r[2] = z0;
+  r[3] = x1;
+  r[4] = y1;
+  r[5] = z1;
+  r[6] = q;
+  r[7] = (double)chunk;
+}
+
+__global__ void __launch_bounds__(128) far_kernel(Geom g, DevPtrs d, double delt)
+{
+  const int n = min(*d.far_count, d.far_cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double* r     = d.far_rec + (int64_t)i * 8;
+    const int     chunk = (int)r[7];
+    const double* lim   = d.clim + chunk * 6;
+    double*       uj    = d.uj + (int64_t)chunk * g.Ng * 4;
+    int           bz = 0, by = 0, bx = 0;
+    const int     My = g.M[1], Mx = g.M[2];
+    auto          add = [&](int kz, int ky, int kx, int k, double v) {
+      if (v != 0.0)
+        atomicAdd(uj + ((int64_t)((bz + kz) * My + (by + ky)) * Mx + (bx + kx)) * 4 + k, v);
+    };
+    esirkepov_deposit<3, 2>(g, lim, r[6], delt, r[0], r[1], r[2], r[3], r[4], r[5], bz, by, bx, add);
+  }
+}
+
+// One slot of the merged particle stream of a row segment: which particle, if any.
+//   idx  index inside the (chunk, species) segment, -1 for the idle slot that pads a cell to ALIGN
+//   sc   species | cell << 8  (cell relative to the segment)
+struct Slot {
+  int idx, sc;
+};
+
+__device__ __forceinline__ Slot stream_slot(const WarpSmem* ws, int t, int Ns)
+{
+  Slot s;
+  s.idx = -1;
+  s.sc  = 0;
+  if (t >= ws->poff[RX])
+    return s;
+  int c = 0;
+#pragma unroll
+  for (int k = 1; k < RX; k++)
+    c += t >= ws->poff[k];
+  int rem = t - ws->poff[c];
+  for (int is = 0; is < Ns; is++) {
+    const int b = ws->pbeg[is * (RX + 1) + c];
+    const int n = ws->pbeg[is * (RX + 1) + c + 1] - b;
+    if (rem >= 0 && rem < n) {
+      s.idx = b + rem;
+      s.sc  = is | (c << 8);
+    }
+    rem -= n; // negative once a species has taken the slot: no later species matches
+  }
+  return s;
+}
+
+// PERM (fused only): a lazy sort is pending -- sorted slot j of a segment still sits in slot perm[j] of
+// xu; the kernel reads through the permutation and writes the pushed particle (all seven components)
+// to slot j of xv, so the reordering costs no pass of its own (the host swaps xu/xv afterwards).
+template <bool FUSED, int Pusher, int Interp, bool PERM>
+__global__ void __launch_bounds__(THREADS, 2)
+row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double*    ftile = reinterpret_cast<double*>(smem_raw);
+  BlockSmem* bs    = reinterpret_cast<BlockSmem*>(smem_raw + sizeof(double) * FTILE);
+  WarpSmem*  wsm   = reinterpret_cast<WarpSmem*>(smem_raw + sizeof(double) * FTILE + sizeof(BlockSmem));
+
+  const int      lane = threadIdx.x & 31;
+  const int      warp = threadIdx.x >> 5;
+  const int      half = lane >> 4;
+  const unsigned FULL = 0xffffffffu;
+  WarpSmem*      ws   = wsm + warp;
+  const LaneMap  lm   = lane_map(lane);
+  const int      Ns   = g.Ns;
+
+  // block -> (chunk, z, y group, x segment)
+  const int nsegx = g.dims[2] / RX;
+  const int nygrp = g.dims[1] / WARPS;
+  int       r     = blockIdx.x;
+  const int lc    = r / (g.dims[0] * nygrp * nsegx);
+  r -= lc * g.dims[0] * nygrp * nsegx;
+  const int jz = r / (nygrp * nsegx);
+  r -= jz * nygrp * nsegx;
+  const int jy0   = (r / nsegx) * WARPS;
+  const int jx0   = (r - (r / nsegx) * nsegx) * RX;
+  const int jy    = jy0 + warp;
+  const int chunk = c0 + lc;
+
+  const double* lim = d.clim + chunk * 6;
+  double*       uj  = d.uj + (int64_t)chunk * g.Ng * 4;
+  const int     My = g.M[1], Mx = g.M[2];
+
+  // ---- the field tile starts travelling (global layout [z][y][x][6], 16-byte asynchronous copies) ----
+  if (FUSED) {
+    const double* uf = d.uf + (int64_t)chunk * g.Ng * 6;
+    const int     gz = jz + g.Lb[0] - 1, gy = jy0 + g.Lb[1] - 1, gx = jx0 + g.Lb[2] - 1;
+    for (int e = threadIdx.x; e < FZ * FY * (FROW / 2); e += THREADS) {
+      const int row = e / (FROW / 2);
+      const int col = e - row * (FROW / 2);
+      const int tz  = row / FY;
+      const int ty  = row - tz * FY;
+      cp_async_16(reinterpret_cast<double2*>(ftile + tz * FSLAB + ty * FROW) + col,
+                  reinterpret_cast<const double2*>(uf + ((int64_t)((gz + tz) * My + (gy + ty)) * Mx + gx) * 6) + col);
+    }
+  }
+  if (threadIdx.x < Ns) {
+    const int    is = threadIdx.x;
+    const double q  = d.qm[2 * is];
+    bs->q[is]       = q;
+    bs->qmdt[is]    = 0.5 * q / d.qm[2 * is + 1] * delt;
+    bs->off[is]     = d.seg_off[chunk * Ns + is];
+  }
+
+  // ---- the stream of this warp's row segment: cell boundaries of every species, padded cell offsets ----
+  const int key0 = jz * g.fsz + jy * g.fsy + jx0;
+  {
+    int cnt = 0;
+    for (int is = 0; is < Ns; is++) {
+      const int* pix = d.pindex + (int64_t)(chunk * Ns + is) * (g.Ng + 1);
+      const int  v   = lane <= RX ? pix[key0 + lane] : 0;
+      if (lane <= RX)
+        ws->pbeg[is * (RX + 1) + lane] = v;
+      const int nxt = __shfl_down_sync(FULL, v, 1);
+      cnt += lane < RX ? nxt - v : 0;
+    }
+    const int padded = (cnt + ALIGN - 1) & ~(ALIGN - 1);
+    int       incl   = padded;
+#pragma unroll
+    for (int dd = 1; dd <= RX; dd <<= 1) {
+      const int t = __shfl_up_sync(FULL, incl, dd);
+      if (lane >= dd)
+        incl += t;
+    }
+    if (lane <= RX)
+      ws->poff[lane] = incl - padded; // lane RX: the length of the stream
+  }
+  for (int i = lane; i < TILE; i += 32)
+    ws->tile[i] = 0.0;
+  __syncthreads(); // stream tables and species constants visible (the field tile is still in flight)
+
+  const int total = ws->poff[RX];
+
+  // ---- first batch: requested before the field tile has landed ----
+  Slot   cur = stream_slot(ws, lane, Ns);
+  double pfx = 0, pfy = 0, pfz = 0, pfux = 0, pfuy = 0, pfuz = 0, pfid = 0;
+  if (FUSED && cur.idx >= 0) {
+    const int64_t off = bs->off[cur.sc & 0xff];
+    const int64_t i   = PERM ? off + d.perm[off + cur.idx] : off + cur.idx;
+    if (PERM)
+      pfid = d.xu[6 * d.pcap + i];
+    pfx  = d.xu[0 * d.pcap + i];
+    pfy  = d.xu[1 * d.pcap + i];
+    pfz  = d.xu[2 * d.pcap + i];
+    pfux = d.xu[3 * d.pcap + i];
+    pfuy = d.xu[4 * d.pcap + i];
+    pfuz = d.xu[5 * d.pcap + i];
+  }
+  if (FUSED) {
+    cp_async_commit_wait();
+    __syncthreads();
+  }
+
+  const double xmin = lim[4], ymin = lim[2], zmin = lim[0];
+  const double xmax = lim[5], ymax = lim[3], zmax = lim[1]; // in registers: the key tests run per particle
+  const double rdx = rc.rd[2], rdy = rc.rd[1], rdz = rc.rd[0];
+  const double dx = rc.del[2], dy = rc.del[1], dz = rc.del[0];
+  // cell-centre ("integer") and cell-edge ("half") grid points of this row, pic/engine/velocity.hpp:304-315
+  const double yig = ymin + 0.5 * dy + (double)jy * dy;
+  const double zig = zmin + 0.5 * dz + (double)jz * dz;
+  const double yh0 = ymin + (double)jy * dy, yh1 = ymin + (double)(jy + 1) * dy;
+  const double zh0 = zmin + (double)jz * dz, zh1 = zmin + (double)(jz + 1) * dz;
+  const double xigrid = xmin + 0.5 * dx, yigrid = ymin + 0.5 * dy, zigrid = zmin + 0.5 * dz;
+
+  Acc acc;
+  acc.clear();
+  int curinfo = -1; // info word of the cell the accumulators belong to (-1: none)
+
+  for (int base = 0; base < total; base += 32) {
+    // the slot this lane handles in the NEXT batch; its permutation entry travels global -> shared
+    // asynchronously while phase 1 runs
+    const Slot nxt = stream_slot(ws, base + 32 + lane, Ns);
+    if (FUSED && PERM && nxt.idx >= 0)
+      cp_async_i32(ws->pbuf + lane, d.perm + bs->off[nxt.sc & 0xff] + nxt.idx);
+
+    // ---------------- phase 1: one particle per lane ----------------
+    int inf = 0;
+    if (cur.idx >= 0) {
+      const int     is = cur.sc & 0xff;
+      const int     jx = cur.sc >> 8;  // old cell in x relative to the segment: given by the sort
+      const int     cx = jx0 + jx;
+      const int64_t i  = bs->off[is] + cur.idx;
+      const double  q  = bs->q[is];
+      double        x0, y0, z0, x1, y1, z1;
+      double        s0x[3], s0y[3], s0z[3];
+      const double  cxf = (double)cx;
+      if (FUSED) {
+        x0        = pfx;
+        y0        = pfy;
+        z0        = pfz;
+        double ux = pfux;
+        double uy = pfuy;
+        double uz = pfuz;
+
+        // weights on the centre grid (MC or WT) and on the edge grid (MC); the particle is in cell
+        // (jz, jy, cx) by construction of the sort
+        double wix[3], wiy[3], wiz[3], h[3], whx[4], why[4], whz[4];
+        const double dix = (x0 - (xigrid + cxf * dx)) * rdx;
+        const double diy = (y0 - yig) * rdy;
+        const double diz = (z0 - zig) * rdz;
+        shape2(dix, s0x);
+        shape2(diy, s0y);
+        shape2(diz, s0z);
+        if (Interp == PICNIX_INTERP_MC) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            wix[k] = s0x[k];
+            wiy[k] = s0y[k];
+            wiz[k] = s0z[k];
+          }
+        } else {
+          shape_wt<2>(x0, xigrid + cxf * dx, rdx, rc.cfl[2], 1 / rc.cfl[2], wix);
+          shape_wt<2>(y0, yig, rdy, rc.cfl[1], 1 / rc.cfl[1], wiy);
+          shape_wt<2>(z0, zig, rdz, rc.cfl[0], 1 / rc.cfl[0], wiz);
+        }
+        // nearest cell edge: the one to the right when the particle sits right of the centre; its
+        // three weights go into the cell-anchored 4-slot array
+        const bool hx = dix >= 0.0, hy = diy >= 0.0, hz = diz >= 0.0;
+        shape2((x0 - (xmin + (cxf + (hx ? 1.0 : 0.0)) * dx)) * rdx, h);
+        shift4(h, hx, whx);
+        shape2((y0 - (hy ? yh1 : yh0)) * rdy, h);
+        shift4(h, hy, why);
+        shape2((z0 - (hz ? zh1 : zh0)) * rdz, h);
+        shift4(h, hz, whz);
+
+        // first stencil point of the cell in the tile; Yee staggering, pic/engine/velocity.hpp:442-447
+        const double* F    = ftile + warp * FROW + jx * 6;
+        const double  qmdt = bs->qmdt[is];
+        double ex = interp_cell<3, 3, 4>(F + 0, wiz, wiy, whx) * qmdt;
+        double ey = interp_cell<3, 4, 3>(F + 1, wiz, why, wix) * qmdt;
+        double ez = interp_cell<4, 3, 3>(F + 2, whz, wiy, wix) * qmdt;
+        double bx = interp_cell<4, 4, 3>(F + 3, whz, why, wix) * qmdt;
+        double by = interp_cell<4, 3, 4>(F + 4, whz, wiy, whx) * qmdt;
+        double bz = interp_cell<3, 4, 4>(F + 5, wiz, why, whx) * qmdt;
+
+        push_momentum<Pusher>(ux, uy, uz, ex, ey, ez, bx, by, bz, rc.cc);
+        x1 = x0;
+        y1 = y0;
+        z1 = z0;
+        push_position(x1, y1, z1, ux, uy, uz, rc.rc, delt);
+        double* xo = PERM ? d.xv : d.xu; // i is the SORTED slot: in place, or the other buffer
+        xo[0 * d.pcap + i] = x1;
+        xo[1 * d.pcap + i] = y1;
+        xo[2 * d.pcap + i] = z1;
+        xo[3 * d.pcap + i] = ux;
+        xo[4 * d.pcap + i] = uy;
+        xo[5 * d.pcap + i] = uz;
+        if (PERM)
+          xo[6 * d.pcap + i] = pfid;
+      } else {
+        x0 = d.xv[0 * d.pcap + i];
+        y0 = d.xv[1 * d.pcap + i];
+        z0 = d.xv[2 * d.pcap + i];
+        x1 = d.xu[0 * d.pcap + i];
+        y1 = d.xu[1 * d.pcap + i];
+        z1 = d.xu[2 * d.pcap + i];
+        shape2((x0 - (xigrid + cxf * dx)) * rdx, s0x);
+        shape2((y0 - yig) * rdy, s0y);
+        shape2((z0 - zig) * rdz, s0z);
+      }
+
+      // new cell: XtensorParticle::count (nix/xtensor_particle.hpp:324-357) and the "after"
+      // weights of the Esirkepov scheme share the digitisation (even order: same cell origin)
+      const int ix1 = digitize(x1, xmin, rdx);
+      const int iy1 = digitize(y1, ymin, rdy);
+      const int iz1 = digitize(z1, zmin, rdz);
+      if (FUSED) {
+        const int seg = chunk * Ns + is;
+        int       key = iz1 * g.fsz + iy1 * g.fsy + ix1;
+        key           = (x1 < xmin || x1 >= xmax) ? g.Ng : key;
+        key           = (y1 < ymin || y1 >= ymax) ? g.Ng : key;
+        key           = (z1 < zmin || z1 >= zmax) ? g.Ng : key;
+        d.gindex[i]   = key;
+        atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, 1);
+        if (key == g.Ng)
+          note_leaver(d, seg, i);
+      }
+
+      double s1x[3], s1y[3], s1z[3];
+      shape2((x1 - (xigrid + (double)ix1 * dx)) * rdx, s1x);
+      shape2((y1 - (yigrid + (double)iy1 * dy)) * rdy, s1y);
+      shape2((z1 - (zigrid + (double)iz1 * dz)) * rdz, s1z);
+      const int shx = ix1 - cx, shy = iy1 - jy, shz = iz1 - jz;
+      if (abs(shx) <= 1 && abs(shy) <= 1 && abs(shz) <= 1) {
+        const AxisFactors fx = window_factors(s0x, s1x, shx);
+        const AxisFactors fy = window_factors(s0y, s1y, shy);
+        const AxisFactors fz = window_factors(s0z, s1z, shz);
+        stage_particle(ws->stg + lane * REC, fx, fy, fz, q, rc.ddt[2], rc.ddt[1], rc.ddt[0]);
+        inf = make_info(jx, fx.w, fy.w, fz.w);
+      } else {
+        defer_far_mover(d, chunk, q, x0, y0, z0, x1, y1, z1);
+      }
+    }
+    ws->info[lane] = inf;
+    if (FUSED && PERM) {
+      cp_async_commit_wait();
+      __syncwarp();
+    }
+    // the phase space of the next batch is requested before phase 2 of the current one, so its HBM
+    // latency hides behind the accumulation loop
+    if (FUSED && nxt.idx >= 0) {
+      const int64_t off = bs->off[nxt.sc & 0xff];
+      const int64_t i   = PERM ? off + ws->pbuf[lane] : off + nxt.idx;
+      if (PERM)
+        pfid = d.xu[6 * d.pcap + i];
+      pfx  = d.xu[0 * d.pcap + i];
+      pfy  = d.xu[1 * d.pcap + i];
+      pfz  = d.xu[2 * d.pcap + i];
+      pfux = d.xu[3 * d.pcap + i];
+      pfuy = d.xu[4 * d.pcap + i];
+      pfuz = d.xu[5 * d.pcap + i];
+    }
+    __syncwarp();
+
+    // ---------------- phase 2: one staged particle per half-warp ----------------
+    // Which passes can take the register-only fast path is decided here once per batch, without
+    // shared-memory loads or votes inside the loop: particle j continues the run of its half-warp
+    // iff it has the majority window and the same info word as its predecessor j-2 (for j < 2: as
+    // the run carried over from the previous batch).  Bit j of `chg` is set otherwise.
+    unsigned chg;
+    {
+      int       pred    = __shfl_up_sync(FULL, inf, 2);
+      const int carried = __shfl_sync(FULL, curinfo, (lane & 1) << 4);
+      if (lane < 2)
+        pred = carried;
+      const bool runs_on = ((inf >> 8) & 0xf) == 0xf && inf == pred;
+      chg                = __ballot_sync(FULL, !runs_on);
+    }
+    const int n     = min(32, total - base);
+    const int npass = (n + 1) >> 1;
+    for (int k = 0; k < npass; k++) {
+      const int     j   = 2 * k + half;
+      const double* rec = ws->stg + j * REC;
+
+      // common case: both particles belong to the cells already being accumulated
+      if (((chg >> (2 * k)) & 3u) == 0u) {
+        accumulate(acc, rec, lm);
+        continue;
+      }
+      const int pinf = ws->info[j];
+
+      const bool valid = (pinf >> 11) & 1;
+      const bool major = valid && ((pinf >> 8) & 7) == 7;
+      const bool minor = valid && !major;
+
+      const bool newcell = major && curinfo != -1 && curinfo != pinf;
+      if (__any_sync(FULL, newcell)) {
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          if (half == hh && newcell)
+            flush(ws->tile, acc, lm, run_index(curinfo));
+          __syncwarp();
+        }
+        if (newcell)
+          acc.clear();
+      }
+      if (major) {
+        curinfo = pinf;
+        accumulate(acc, rec, lm);
+      }
+      if (__any_sync(FULL, minor)) {
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          if (half == hh && minor)
+            deposit_direct(ws->tile, rec, lm, run_index(pinf));
+          __syncwarp();
+        }
+      }
+    }
+    __syncwarp();
+    cur = nxt;
+  }
+
+  // end of the segment: the accumulators of both half-warps
+#pragma unroll
+  for (int hh = 0; hh < 2; hh++) {
+    if (half == hh && curinfo != -1)
+      flush(ws->tile, acc, lm, run_index(curinfo));
+    __syncwarp();
+  }
+
+  // warp tile -> global current: one fp64 reduction per non-zero tile value; tile and uj both keep
+  // the four components of a point together, so a (z, y) line of the tile is one contiguous run of uj
+  const int gz0 = jz + g.Lb[0] - 2, gy0 = jy + g.Lb[1] - 2, gx0 = jx0 + g.Lb[2] - 2;
+  for (int row = 0; row < 25; row++) {
+    const int     tz  = row / 5;
+    const int     ty  = row - tz * 5;
+    const double* src = ws->tile + 4 * (tz * SZ + ty * SY);
+    double*       dst = uj + ((int64_t)((gz0 + tz) * My + (gy0 + ty)) * Mx + gx0) * 4;
+    for (int e = lane; e < 4 * XS; e += 32) {
+      const double v = src[e];
+      if (v != 0.0)
+        atomicAdd(dst + e, v);
+    }
+  }
+}
+
+template <bool FUSED>
+int launch_row_kernel(picnix_arena* a, int c0, int cn, double delt)
+{
+  const Geom& g      = a->g;
+  const int   blocks = g.dims[0] * (g.dims[1] / WARPS) * (g.dims[2] / RX) * cn;
+  const int   key    = FUSED ? a->cfg.pusher * 2 + a->cfg.interp : 0;
+  // a pending lazy sort is consumed by the fused kernel itself when it covers the whole arena;
+  // everything else (partial ranges, deposit only) wants physically ordered arrays
+  const bool  perm   = FUSED && a->perm_pending && c0 == 0 && cn == g.nchunk;
+  if (!perm) {
+    int status = materialize_sort(a);
+    if (status != PICNIX_OK)
+      return status;
+  }
+
+  RowConst rc;
+  for (int i = 0; i < 3; i++) {
+    rc.rd[i]  = 1 / g.del[i];
+    rc.del[i] = g.del[i];
+    rc.ddt[i] = g.del[i] / delt;
+    rc.cfl[i] = g.cc * delt / g.del[i];
+  }
+  rc.cc   = g.cc;
+  rc.rc   = 1 / g.cc;
+  rc.delt = delt;
+  PICNIX_CUDA(a, cudaMemsetAsync(a->d.far_count, 0, sizeof(int), a->stream));
+
+#define PICNIX_ROW_LAUNCH(P, I)                                                                    \
+  if (perm) {                                                                                      \
+    auto kern = row_push_kernel<FUSED, P, I, FUSED>;                                               \
+    PICNIX_CUDA(a, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                        (int)SMEM_BYTES));                                         \
+    kern<<<blocks, THREADS, SMEM_BYTES, a->stream>>>(g, a->d, rc, c0, cn, delt);                   \
+  } else {                                                                                         \
+    auto kern = row_push_kernel<FUSED, P, I, false>;                                               \
+    PICNIX_CUDA(a, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                        (int)SMEM_BYTES));                                         \
+    kern<<<blocks, THREADS, SMEM_BYTES, a->stream>>>(g, a->d, rc, c0, cn, delt);                   \
+  }
+  if constexpr (!FUSED) {
+    // deposit only: pusher and interpolation do not enter, one instantiation serves all
+    PICNIX_ROW_LAUNCH(PICNIX_PUSHER_BORIS, PICNIX_INTERP_MC);
+  } else {
+    switch (key) {
+    case 0:
+      PICNIX_ROW_LAUNCH(PICNIX_PUSHER_BORIS, PICNIX_INTERP_MC);
+      break;
+    case 1:
+      PICNIX_ROW_LAUNCH(PICNIX_PUSHER_BORIS, PICNIX_INTERP_WT);
+      break;
+    case 2:
+      PICNIX_ROW_LAUNCH(PICNIX_PUSHER_VAY, PICNIX_INTERP_MC);
+      break;
+    case 3:
+      PICNIX_ROW_LAUNCH(PICNIX_PUSHER_VAY, PICNIX_INTERP_WT);
+      break;
+    case 4:
+      PICNIX_ROW_LAUNCH(PICNIX_PUSHER_HIGUERA_CARY, PICNIX_INTERP_MC);
+      break;
+    default:
+      PICNIX_ROW_LAUNCH(PICNIX_PUSHER_HIGUERA_CARY, PICNIX_INTERP_WT);
+      break;
+    }
+  }
+#undef PICNIX_ROW_LAUNCH
+  far_kernel<<<64, 128, 0, a->stream>>>(g, a->d, delt);
+  a->kernel_launches += 2;
+  if (perm) {
+    // the kernel wrote the pushed particles in sorted order into xv
+    std::swap(a->d.xu, a->d.xv);
+    a->perm_pending = false;
+  }
+  return check_cuda(a, cudaGetLastError(), "row_push_kernel");
+}
+
+} // namespace
+
+bool row_push_applies(const picnix_arena* a)
+{
+  return a->g.Ns <= rowtile::MAXNS;
+}
+
+int launch_deposit_rows_v2(picnix_arena* a, int c0, int cn, double delt)
+{
+  return launch_row_kernel<false>(a, c0, cn, delt);
+}
+
+int launch_row_fused_v2(picnix_arena* a, int c0, int cn, double delt)
+{
+  return launch_row_kernel<true>(a, c0, cn, delt);
+}
+
+} // namespace picnix

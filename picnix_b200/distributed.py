@@ -184,10 +184,10 @@ def rebalance_in_process(sims, new_boundary, make_sim):
 class DistributedSim(CudaSim):
     """CudaSim whose chunk ids are split over `world` ranks like the reference's MPI ranks."""
 
-    def __init__(self, ndims, cdims, Ns, cc, rank=0, world=1, block_layout=None, boundary=None,
-                 async_migration=True, **kw):
+    def __init__(self, ndims, cdims, Ns, cc, rank=0, world=1, boundary=None, async_migration=True, **kw):
         super().__init__(ndims, cdims, Ns, cc, nrank=world, rank=rank, boundary=boundary, **kw)
         self.rank, self.world = rank, world
+        self._async_migration = async_migration
         if os.environ.get("PICNIX_ASYNC_MIGRATION", "1") == "0":
             async_migration = False  # escape hatch: the synchronous count exchange of the first version
         if world > 1 and async_migration:
@@ -235,7 +235,14 @@ class DistributedSim(CudaSim):
             dist.all_reduce(ob)
         old_boundary = [int(v) for v in ob.cpu()]
 
-        new = DistributedSim(rank=self.rank, world=self.world, boundary=new_boundary, **self._ctor)
+        new = DistributedSim(rank=self.rank, world=self.world, boundary=new_boundary,
+                             async_migration=self._async_migration, **self._ctor)
+        # the new arena keeps enqueuing on the caller's stream and keeps the tuning switches
+        if self._stream_ptr is not None:
+            new.set_stream(self._stream_ptr)
+        for key, value in self._options.items():
+            if key != "async_migration":
+                new.set_option(key, value)
         new.set_capacity(_capacities(np_all[new_boundary[self.rank]:new_boundary[self.rank + 1]],
                                      self.cfg.buffer_ratio))
         for isp, (q, m) in self._species.items():

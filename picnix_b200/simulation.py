@@ -59,6 +59,7 @@ class CudaSim:
         self._capacity_set = False
         self._species = {}
         self._stream_ptr = None  # the arena owns its stream until set_stream() is called
+        self._options = {}       # set_option history: carried over when the arena is rebuilt (rebalance)
         self._ctor = dict(ndims=tuple(ndims), cdims=tuple(cdims), Ns=Ns, cc=cc, delh=delh, order=order,
                           pusher=pusher, interp=interp, periodic=tuple(periodic), friedman=friedman,
                           buffer_ratio=buffer_ratio)
@@ -84,6 +85,7 @@ class CudaSim:
 
     def set_option(self, key, value):
         self._check(self.lib.picnix_cuda_set_option(self.h, key.encode(), int(value)))
+        self._options[key] = int(value)
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.picnix_cuda_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))

@@ -77,13 +77,43 @@ def counts_equal(a, b):
     return True
 
 
-def cells_consistent(sim):
-    """Every particle sits in the cell range pindex assigns to its key (sortedness)."""
-    for ic in range(sim.nchunk):
+def chunk_limits(sim, ndims, cdims, ic, delh=1.0, chunk_id_begin=0):
+    """(zmin, ymin, xmin) of local chunk `ic` from the chunk map (Chunk::set_coordinate)."""
+    _, coord = sim.chunkmap()
+    cx, cy, cz = (int(v) for v in coord[chunk_id_begin + ic])
+    dims = problems.chunk_dims(ndims, cdims)
+    return cz * dims[0] * delh, cy * dims[1] * delh, cx * dims[2] * delh
+
+
+def cells_consistent(sim, ndims=None, cdims=None, delh=1.0, chunk_id_begin=0, chunks=None):
+    """Every particle sits in the slot range pindex assigns to the key of its position (sortedness):
+    the keys are recomputed here from the downloaded positions and the chunk limits
+    (XtensorParticle::count, nix/xtensor_particle.hpp:324-357; even orders) and
+    pindex[key] <= slot < pindex[key + 1] is asserted for every slot.  Without ndims/cdims only
+    pindex[-1] == Np and monotonicity are checked."""
+    for ic in (range(sim.nchunk) if chunks is None else chunks):
         for isp in range(sim.Ns):
             n = sim.get_np(ic, isp)
-            pindex = sim.get_pindex(ic, isp)
-            if pindex[-1] != n:
+            pindex = sim.get_pindex(ic, isp).astype(np.int64)
+            if pindex[-1] != n or pindex[0] != 0 or np.any(np.diff(pindex) < 0):
+                return False
+            if ndims is None or n == 0:
+                continue
+            xu = sim.get_particles(ic, isp, 0, n)
+            zmin, ymin, xmin = chunk_limits(sim, ndims, cdims, ic, delh, chunk_id_begin)
+            dims = problems.chunk_dims(ndims, cdims)
+            has = [d > 1 for d in dims]
+            # flatindex strides, nix/xtensor_particle.hpp:231-238 (ignorable dimensions have one cell)
+            sy = dims[2] + 1 if has[2] else 2
+            sz = sy * ((dims[1] + 1) if has[1] else 2)
+            ix = np.floor((xu[:, 0] - xmin) / delh).astype(np.int64) if has[2] else np.zeros(n, np.int64)
+            iy = np.floor((xu[:, 1] - ymin) / delh).astype(np.int64) if has[1] else np.zeros(n, np.int64)
+            iz = np.floor((xu[:, 2] - zmin) / delh).astype(np.int64) if has[0] else np.zeros(n, np.int64)
+            key = iz * sz + iy * sy + ix
+            slot = np.arange(n, dtype=np.int64)
+            if np.any(key < 0) or np.any(key >= pindex.size - 1):
+                return False
+            if np.any(slot < pindex[key]) or np.any(slot >= pindex[key + 1]):
                 return False
     return True
 

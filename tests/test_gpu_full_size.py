@@ -9,6 +9,7 @@ particles): size-independent properties of the step, since the reference cannot 
 import numpy as np
 import pytest
 
+from helpers import cells_consistent
 from picnix_b200 import problems
 
 pytestmark = pytest.mark.gpu
@@ -45,6 +46,8 @@ def test_full_size_conservation(sim):
     for ic in (0, 137, sim.nchunk - 1):
         for isp in range(2):
             assert sim.get_pindex(ic, isp)[-1] == np_all[ic, isp]
+    # every slot lies in the pindex range of the key recomputed from its position
+    assert cells_consistent(sim, (CELLS,) * 3, (CELLS // CHUNK,) * 3, chunks=(0, 137, sim.nchunk - 1))
     de = sim.get_diverror()
     scale = np.abs(sim.get_field(0, 1)[..., 0]).max() * CHUNK ** 3  # |rho| summed over a chunk
     assert np.abs(de[:, 0]).max() < 1e-9 * max(scale, 1.0)

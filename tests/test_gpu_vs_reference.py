@@ -15,8 +15,8 @@ integer results (Np, pindex, keys) must be bit-exact.
 import numpy as np
 import pytest
 
-from helpers import (FIELD_FF, FIELD_UF, FIELD_UJ, MODE_CUR, MODE_EMF, MODE_PARTICLE, counts_equal, field_err,
-                     keys_equal, particle_err)
+from helpers import (FIELD_FF, FIELD_UF, FIELD_UJ, MODE_CUR, MODE_EMF, MODE_PARTICLE, cells_consistent,
+                     counts_equal, field_err, keys_equal, particle_err)
 from oracle import ref_backend
 from picnix_b200 import problems
 
@@ -27,6 +27,9 @@ CASES = {
     "t3d": ((16, 16, 16), (2, 2, 2), problems.THERMAL_SPECIES, (8, 8), 10.0, (5.0, 0.0, 0.0)),
     "t2d": ((1, 32, 32), (1, 2, 4), problems.THERMAL_SPECIES, (16, 16), 10.0, (5.0, 0.0, 0.0)),
     "ts1d": ((1, 1, 64), (1, 1, 8), problems.TWOSTREAM_SPECIES, (16, 16, 32), 50.0, (10.0, 0.0, 0.0)),
+    # the benchmark's chunk shape and density (bench.py): 16^3-cell chunks, 2 x 32 ppc -- both x segments of
+    # a row, four y groups per z, several full batches per row segment and species in the tiled kernel
+    "t3d_bench": ((32, 32, 32), (2, 2, 2), problems.THERMAL_SPECIES, (32, 32), 10.0, (5.0, 0.0, 0.0)),
 }
 
 
@@ -151,6 +154,49 @@ def test_multistep(case, nstep):
     # conservation residuals: sum(div E - rho) and sum(div B) at round-off on both sides
     de_ref, de_gpu = ref.get_diverror().sum(0), gpu.get_diverror().sum(0)
     assert abs(de_gpu[0]) < 1e-10 and abs(de_ref[0]) < 1e-10
+    assert abs(de_gpu[1]) < 1e-10 and abs(de_ref[1]) < 1e-10
+
+
+def test_benchmark_shape_phase_by_phase():
+    """16^3-cell chunks at 2 x 32 ppc (the shape bench.py times): one fused tiled push + deposit on
+    cell-sorted particles against the reference's three separate calls -- velocity, position, keys,
+    current -- then the J halo, the migration and the sort."""
+    ref, gpu = make_pair("t3d_bench")
+    dt = 0.05
+    ref.push_velocity(dt)
+    ref.push_position(dt)
+    ref.deposit_current(dt)
+    gpu.push_deposit_fused(dt)
+    dx, du, same = particle_err(gpu, ref, scale_x=32.0, scale_u=10.0)
+    assert same and dx < 1e-14 and du < 1e-13
+    assert keys_equal(gpu, ref)
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-12
+    for sim in (ref, gpu):
+        sim.exchange(MODE_CUR)
+        sim.exchange(MODE_PARTICLE)
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-12
+    assert counts_equal(gpu, ref)
+    assert cells_consistent(gpu, CASES["t3d_bench"][0], CASES["t3d_bench"][1])
+
+
+@pytest.mark.parametrize("lazy", [1, 0])
+def test_benchmark_shape_multistep(lazy):
+    """20 whole steps at the benchmark's chunk shape through picnix_cuda_step (fused tiled kernel;
+    with the lazy sort the reordering rides on the next push) against PicApplication's schedule run
+    by the reference: Np / pindex bit-exact, fields <= 1e-10, phase space matched by id <= 1e-11."""
+    ref, gpu = make_pair("t3d_bench", perturb=None)
+    gpu.set_option("lazy_sort", lazy)
+    ref.step(0.05, 20)
+    gpu.step(0.05, 20)
+    gpu.synchronize()
+    assert counts_equal(gpu, ref)
+    assert field_err(gpu, ref, FIELD_UF) < 1e-10
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-10
+    dx, du, same = particle_err(gpu, ref, scale_x=32.0, scale_u=10.0)
+    assert same and dx < 1e-11 and du < 1e-11
+    assert cells_consistent(gpu, CASES["t3d_bench"][0], CASES["t3d_bench"][1])
+    de_ref, de_gpu = ref.get_diverror().sum(0), gpu.get_diverror().sum(0)
+    assert abs(de_gpu[0]) < 1e-9 and abs(de_ref[0]) < 1e-9
     assert abs(de_gpu[1]) < 1e-10 and abs(de_ref[1]) < 1e-10
 
 
