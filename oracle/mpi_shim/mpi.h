@@ -52,6 +52,8 @@ struct MPI_Status {
 #define MPI_DOUBLE 8
 #define MPI_INT64_T 8
 #define MPI_LONG_LONG 8
+/* derived datatypes (MPI_Type_contiguous / create_hindexed / create_subarray) get handles >= this */
+#define PICNIX_SHIM_DERIVED_BASE 0x10000
 
 #define MPI_SUM 1
 #define MPI_LAND 2
@@ -65,6 +67,7 @@ struct MPI_Status {
 
 #define MPI_COMM_TYPE_SHARED 1
 #define MPI_ORDER_C 0
+#define MPI_ORDER_FORTRAN 1
 #define MPI_MODE_RDONLY 1
 #define MPI_MODE_WRONLY 2
 #define MPI_MODE_CREATE 4
@@ -92,6 +95,11 @@ int MPI_Barrier(MPI_Comm);
 int MPI_Bcast(void* buf, int count, MPI_Datatype, int root, MPI_Comm);
 int MPI_Allreduce(const void* sbuf, void* rbuf, int count, MPI_Datatype, MPI_Op, MPI_Comm);
 int MPI_Reduce(const void* sbuf, void* rbuf, int count, MPI_Datatype, MPI_Op, int root, MPI_Comm);
+int MPI_Allgather(const void* sbuf, int scount, MPI_Datatype, void* rbuf, int rcount, MPI_Datatype, MPI_Comm);
+int MPI_Gather(const void* sbuf, int scount, MPI_Datatype, void* rbuf, int rcount, MPI_Datatype, int root,
+               MPI_Comm);
+int MPI_Gatherv(const void* sbuf, int scount, MPI_Datatype, void* rbuf, const int* rcounts, const int* displs,
+                MPI_Datatype, int root, MPI_Comm);
 int MPI_Allgatherv(const void* sbuf, int scount, MPI_Datatype, void* rbuf, const int* rcounts,
                    const int* displs, MPI_Datatype, MPI_Comm);
 int MPI_Isend(const void* buf, int count, MPI_Datatype, int dest, int tag, MPI_Comm, MPI_Request*);
@@ -102,6 +110,30 @@ int MPI_Type_size(MPI_Datatype, int* size);
 int MPI_Wait(MPI_Request*, MPI_Status*);
 int MPI_Waitall(int n, MPI_Request*, MPI_Status*);
 int MPI_Testall(int n, MPI_Request*, int* flag, MPI_Status*);
+
+/* derived datatypes: enough for nix/nixio.cpp (one contiguous block per process) */
+int MPI_Type_contiguous(int count, MPI_Datatype oldtype, MPI_Datatype* newtype);
+int MPI_Type_create_hindexed(int count, const int* blocklens, const MPI_Aint* displs, MPI_Datatype oldtype,
+                             MPI_Datatype* newtype);
+int MPI_Type_create_subarray(int ndim, const int* gshape, const int* lshape, const int* offset, int order,
+                             MPI_Datatype oldtype, MPI_Datatype* newtype);
+int MPI_Type_commit(MPI_Datatype*);
+int MPI_Type_free(MPI_Datatype*);
+
+/* MPI-IO on POSIX files, single process: the *_all calls write the process' block at
+ * view displacement + block offset, the *_at calls at view displacement + offset * etype size */
+int MPI_File_open(MPI_Comm, const char* filename, int amode, MPI_Info, MPI_File* fh);
+int MPI_File_close(MPI_File* fh);
+int MPI_File_delete(const char* filename, MPI_Info);
+int MPI_File_seek(MPI_File fh, MPI_Offset offset, int whence);
+int MPI_File_get_size(MPI_File fh, MPI_Offset* size);
+int MPI_File_get_position(MPI_File fh, MPI_Offset* pos);
+int MPI_File_set_view(MPI_File fh, MPI_Offset disp, MPI_Datatype etype, MPI_Datatype filetype,
+                      const char* datarep, MPI_Info);
+int MPI_File_iread_all(MPI_File fh, void* buf, int count, MPI_Datatype, MPI_Request*);
+int MPI_File_iwrite_all(MPI_File fh, const void* buf, int count, MPI_Datatype, MPI_Request*);
+int MPI_File_iread_at(MPI_File fh, MPI_Offset offset, void* buf, int count, MPI_Datatype, MPI_Request*);
+int MPI_File_iwrite_at(MPI_File fh, MPI_Offset offset, const void* buf, int count, MPI_Datatype, MPI_Request*);
 
 /* shim-only helper: drop every undelivered message and pending request */
 void picnix_mpi_shim_reset(void);

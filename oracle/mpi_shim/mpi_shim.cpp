@@ -19,6 +19,10 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 namespace
 {
 struct Pending {
@@ -36,6 +40,45 @@ std::map<Key, std::deque<std::vector<uint8_t>>>    g_mailbox;
 std::vector<Pending>                               g_pending;
 std::vector<int>                                   g_free_slots;
 std::atomic<int>                                   g_next_comm{1};
+
+// derived datatypes: one contiguous block of `bytes` at byte offset `offset` inside the file view
+struct Derived {
+  long long bytes;
+  long long offset;
+};
+std::vector<Derived> g_types;
+
+long long type_bytes(MPI_Datatype t)
+{
+  if (t < PICNIX_SHIM_DERIVED_BASE)
+    return t;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return g_types[t - PICNIX_SHIM_DERIVED_BASE].bytes;
+}
+
+long long type_offset(MPI_Datatype t)
+{
+  if (t < PICNIX_SHIM_DERIVED_BASE)
+    return 0;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return g_types[t - PICNIX_SHIM_DERIVED_BASE].offset;
+}
+
+MPI_Datatype new_type(long long bytes, long long offset)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  g_types.push_back(Derived{bytes, offset});
+  return PICNIX_SHIM_DERIVED_BASE + (int)g_types.size() - 1;
+}
+
+struct ShimFile {
+  int       fd = -1;
+  long long pos = 0;        // individual file pointer, bytes
+  long long view_disp = 0;  // MPI_File_set_view: displacement
+  long long view_etype = 1; //                    etype size
+  long long view_block = 0; //                    offset of this process' block inside the filetype
+};
+std::vector<ShimFile> g_files;
 
 // try to complete a pending receive; caller holds the mutex
 bool try_complete(int slot)
@@ -169,6 +212,221 @@ int MPI_Reduce(const void* sbuf, void* rbuf, int count, MPI_Datatype type, MPI_O
   if (sbuf != MPI_IN_PLACE)
     std::memcpy(rbuf, sbuf, (size_t)count * type);
   return MPI_SUCCESS;
+}
+
+int MPI_Allgather(const void* sbuf, int scount, MPI_Datatype type, void* rbuf, int, MPI_Datatype, MPI_Comm)
+{
+  if (sbuf != MPI_IN_PLACE)
+    std::memcpy(rbuf, sbuf, (size_t)scount * type_bytes(type));
+  return MPI_SUCCESS;
+}
+
+int MPI_Gather(const void* sbuf, int scount, MPI_Datatype type, void* rbuf, int, MPI_Datatype, int, MPI_Comm)
+{
+  if (sbuf != MPI_IN_PLACE)
+    std::memcpy(rbuf, sbuf, (size_t)scount * type_bytes(type));
+  return MPI_SUCCESS;
+}
+
+int MPI_Gatherv(const void* sbuf, int scount, MPI_Datatype type, void* rbuf, const int*, const int* displs,
+                MPI_Datatype, int, MPI_Comm)
+{
+  if (sbuf != MPI_IN_PLACE)
+    std::memcpy((uint8_t*)rbuf + (size_t)(displs ? displs[0] : 0) * type_bytes(type), sbuf,
+                (size_t)scount * type_bytes(type));
+  return MPI_SUCCESS;
+}
+
+int MPI_Type_contiguous(int count, MPI_Datatype oldtype, MPI_Datatype* newtype)
+{
+  *newtype = new_type((long long)count * type_bytes(oldtype), 0);
+  return MPI_SUCCESS;
+}
+
+int MPI_Type_create_hindexed(int count, const int* blocklens, const MPI_Aint* displs, MPI_Datatype oldtype,
+                             MPI_Datatype* newtype)
+{
+  if (count != 1) {
+    std::fprintf(stderr, "[mpi_shim] MPI_Type_create_hindexed: only one block is supported\n");
+    std::abort();
+  }
+  *newtype = new_type((long long)blocklens[0] * type_bytes(oldtype), displs[0]);
+  return MPI_SUCCESS;
+}
+
+int MPI_Type_create_subarray(int ndim, const int* gshape, const int* lshape, const int* offset, int,
+                             MPI_Datatype oldtype, MPI_Datatype* newtype)
+{
+  long long n = 1;
+  for (int i = 0; i < ndim; i++) {
+    if (gshape[i] != lshape[i] || offset[i] != 0) {
+      std::fprintf(stderr, "[mpi_shim] MPI_Type_create_subarray: one process owns the whole array\n");
+      std::abort();
+    }
+    n *= lshape[i];
+  }
+  *newtype = new_type(n * type_bytes(oldtype), 0);
+  return MPI_SUCCESS;
+}
+
+int MPI_Type_commit(MPI_Datatype*)
+{
+  return MPI_SUCCESS;
+}
+
+int MPI_Type_free(MPI_Datatype*)
+{
+  return MPI_SUCCESS; // handles are never reused: sizes stay valid for requests in flight
+}
+
+int MPI_File_open(MPI_Comm, const char* filename, int amode, MPI_Info, MPI_File* fh)
+{
+  int flags = 0;
+  if (amode & MPI_MODE_RDWR)
+    flags |= O_RDWR;
+  else if (amode & MPI_MODE_WRONLY)
+    flags |= O_WRONLY;
+  else
+    flags |= O_RDONLY;
+  if (amode & MPI_MODE_CREATE)
+    flags |= O_CREAT;
+  const int fd = ::open(filename, flags, 0644);
+  if (fd < 0)
+    return 1;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  ShimFile                    f;
+  f.fd = fd;
+  g_files.push_back(f);
+  *fh = (int)g_files.size() - 1;
+  return MPI_SUCCESS;
+}
+
+int MPI_File_close(MPI_File* fh)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (*fh >= 0 && *fh < (int)g_files.size() && g_files[*fh].fd >= 0) {
+    ::close(g_files[*fh].fd);
+    g_files[*fh].fd = -1;
+  }
+  *fh = -1;
+  return MPI_SUCCESS;
+}
+
+int MPI_File_delete(const char* filename, MPI_Info)
+{
+  return ::unlink(filename) == 0 ? MPI_SUCCESS : 1;
+}
+
+int MPI_File_seek(MPI_File fh, MPI_Offset offset, int whence)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  ShimFile&                   f = g_files[fh];
+  if (whence == MPI_SEEK_SET)
+    f.pos = offset * f.view_etype;
+  else if (whence == MPI_SEEK_CUR)
+    f.pos += offset * f.view_etype;
+  else {
+    struct stat st;
+    ::fstat(f.fd, &st);
+    f.pos = st.st_size - f.view_disp + offset * f.view_etype;
+  }
+  return MPI_SUCCESS;
+}
+
+int MPI_File_get_size(MPI_File fh, MPI_Offset* size)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  struct stat                 st;
+  ::fstat(g_files[fh].fd, &st);
+  *size = st.st_size;
+  return MPI_SUCCESS;
+}
+
+int MPI_File_get_position(MPI_File fh, MPI_Offset* pos)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  *pos = g_files[fh].pos / g_files[fh].view_etype;
+  return MPI_SUCCESS;
+}
+
+int MPI_File_set_view(MPI_File fh, MPI_Offset disp, MPI_Datatype etype, MPI_Datatype filetype, const char*,
+                      MPI_Info)
+{
+  const long long es = type_bytes(etype), bo = type_offset(filetype);
+  std::lock_guard<std::mutex> lock(g_mutex);
+  ShimFile&                   f = g_files[fh];
+  f.view_disp  = disp;
+  f.view_etype = es;
+  f.view_block = bo;
+  f.pos        = 0;
+  return MPI_SUCCESS;
+}
+
+namespace
+{
+int file_rw(MPI_File fh, long long where, void* buf, long long bytes, bool write)
+{
+  int fd;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    fd = g_files[fh].fd;
+  }
+  uint8_t*  p    = static_cast<uint8_t*>(buf);
+  long long done = 0;
+  while (done < bytes) {
+    const ssize_t n = write ? ::pwrite(fd, p + done, bytes - done, where + done)
+                            : ::pread(fd, p + done, bytes - done, where + done);
+    if (n <= 0)
+      return 1;
+    done += n;
+  }
+  return MPI_SUCCESS;
+}
+} // namespace
+
+int MPI_File_iread_all(MPI_File fh, void* buf, int count, MPI_Datatype type, MPI_Request* req)
+{
+  *req = MPI_REQUEST_NULL;
+  long long where;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    where = g_files[fh].view_disp + g_files[fh].view_block;
+  }
+  return file_rw(fh, where, buf, (long long)count * type_bytes(type), false);
+}
+
+int MPI_File_iwrite_all(MPI_File fh, const void* buf, int count, MPI_Datatype type, MPI_Request* req)
+{
+  *req = MPI_REQUEST_NULL;
+  long long where;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    where = g_files[fh].view_disp + g_files[fh].view_block;
+  }
+  return file_rw(fh, where, const_cast<void*>(buf), (long long)count * type_bytes(type), true);
+}
+
+int MPI_File_iread_at(MPI_File fh, MPI_Offset offset, void* buf, int count, MPI_Datatype type, MPI_Request* req)
+{
+  *req = MPI_REQUEST_NULL;
+  long long where;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    where = g_files[fh].view_disp + offset * g_files[fh].view_etype;
+  }
+  return file_rw(fh, where, buf, (long long)count * type_bytes(type), false);
+}
+
+int MPI_File_iwrite_at(MPI_File fh, MPI_Offset offset, const void* buf, int count, MPI_Datatype type,
+                       MPI_Request* req)
+{
+  *req = MPI_REQUEST_NULL;
+  long long where;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    where = g_files[fh].view_disp + offset * g_files[fh].view_etype;
+  }
+  return file_rw(fh, where, const_cast<void*>(buf), (long long)count * type_bytes(type), true);
 }
 
 int MPI_Allgatherv(const void* sbuf, int scount, MPI_Datatype type, void* rbuf, const int*,

@@ -182,51 +182,105 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
   }
   for (int i = lane; i < TILE; i += 32)
     ws->tile[i] = 0.0;
+  for (int i = lane; i < REC + 2; i += 32)
+    ws->zero[i] = 0.0;
   __syncthreads(); // stream tables and species constants visible (the field tile is still in flight)
 
   const int total = ws->poff[RX];
 
-  // ---- first batch: requested before the field tile has landed ----
-  Slot   cur = stream_slot(ws, lane, Ns);
-  double pfx = 0, pfy = 0, pfz = 0, pfux = 0, pfuy = 0, pfuz = 0, pfid = 0;
-  if (FUSED && cur.idx >= 0) {
-    const int64_t off = bs->off[cur.sc & 0xff];
-    const int64_t i   = PERM ? off + d.perm[off + cur.idx] : off + cur.idx;
-    if (PERM)
-      pfid = d.xu[6 * d.pcap + i];
-    pfx  = d.xu[0 * d.pcap + i];
-    pfy  = d.xu[1 * d.pcap + i];
-    pfz  = d.xu[2 * d.pcap + i];
-    pfux = d.xu[3 * d.pcap + i];
-    pfuy = d.xu[4 * d.pcap + i];
-    pfuz = d.xu[5 * d.pcap + i];
-  }
+  // ---- first batch: its phase space travels global -> shared behind the field tile; so do the
+  // permutation entries of the second batch (everything asynchronous, nothing held in registers) ----
+  Slot cur = stream_slot(ws, lane, Ns);
+  Slot nxt = stream_slot(ws, 32 + lane, Ns);
   if (FUSED) {
+    if (cur.idx >= 0) {
+      const int64_t off = bs->off[cur.sc & 0xff];
+      const int64_t i   = PERM ? off + d.perm[off + cur.idx] : off + cur.idx;
+#pragma unroll
+      for (int k = 0; k < (PERM ? 7 : 6); k++)
+        cp_async_f64(&ws->pfb[k][lane], d.xu + k * d.pcap + i);
+    }
+    if (PERM && nxt.idx >= 0)
+      cp_async_i32(ws->pbuf + lane, d.perm + bs->off[nxt.sc & 0xff] + nxt.idx);
     cp_async_commit_wait();
     __syncthreads();
   }
 
-  const double xmin = lim[4], ymin = lim[2], zmin = lim[0];
-  const double xmax = lim[5], ymax = lim[3], zmax = lim[1]; // in registers: the key tests run per particle
   const double rdx = rc.rd[2], rdy = rc.rd[1], rdz = rc.rd[0];
   const double dx = rc.del[2], dy = rc.del[1], dz = rc.del[0];
-  // cell-centre ("integer") and cell-edge ("half") grid points of this row, pic/engine/velocity.hpp:304-315
-  const double yig = ymin + 0.5 * dy + (double)jy * dy;
-  const double zig = zmin + 0.5 * dz + (double)jz * dz;
-  const double yh0 = ymin + (double)jy * dy, yh1 = ymin + (double)(jy + 1) * dy;
-  const double zh0 = zmin + (double)jz * dz, zh1 = zmin + (double)(jz + 1) * dz;
-  const double xigrid = xmin + 0.5 * dx, yigrid = ymin + 0.5 * dy, zigrid = zmin + 0.5 * dz;
+  // The chunk limits and the grid points of this row are needed a few times per batch.  Held in
+  // registers they push the kernel over the register file and get spilled to LOCAL memory -- which, with
+  // almost all of the SM's memory configured as shared, means a trip to L2.  They live in shared memory
+  // instead and are re-read at every use (volatile: the compiler must not cache them in registers).
+  //   cell-centre ("integer") and cell-edge ("half") grid points: pic/engine/velocity.hpp:304-315
+  if (lane == 0) {
+    const double xmin0 = lim[4], ymin0 = lim[2], zmin0 = lim[0];
+    ws->rowc[0]  = xmin0;
+    ws->rowc[1]  = ymin0;
+    ws->rowc[2]  = zmin0;
+    ws->rowc[3]  = lim[5];
+    ws->rowc[4]  = lim[3];
+    ws->rowc[5]  = lim[1];
+    ws->rowc[6]  = ymin0 + 0.5 * dy + (double)jy * dy; // yig
+    ws->rowc[7]  = zmin0 + 0.5 * dz + (double)jz * dz; // zig
+    ws->rowc[8]  = ymin0 + (double)jy * dy;            // yh0
+    ws->rowc[9]  = ymin0 + (double)(jy + 1) * dy;      // yh1
+    ws->rowc[10] = zmin0 + (double)jz * dz;            // zh0
+    ws->rowc[11] = zmin0 + (double)(jz + 1) * dz;      // zh1
+    ws->rowc[12] = xmin0 + 0.5 * dx;                   // xigrid
+    ws->rowc[13] = ymin0 + 0.5 * dy;                   // yigrid
+    ws->rowc[14] = zmin0 + 0.5 * dz;                   // zigrid
+  }
+  __syncwarp();
+  const volatile double* rowc = ws->rowc;
+#define xmin rowc[0]
+#define ymin rowc[1]
+#define zmin rowc[2]
+#define xmax rowc[3]
+#define ymax rowc[4]
+#define zmax rowc[5]
+#define yig rowc[6]
+#define zig rowc[7]
+#define yh0 rowc[8]
+#define yh1 rowc[9]
+#define zh0 rowc[10]
+#define zh1 rowc[11]
+#define xigrid rowc[12]
+#define yigrid rowc[13]
+#define zigrid rowc[14]
 
   Acc acc;
   acc.clear();
   int curinfo = -1; // info word of the cell the accumulators belong to (-1: none)
 
   for (int base = 0; base < total; base += 32) {
-    // the slot this lane handles in the NEXT batch; its permutation entry travels global -> shared
-    // asynchronously while phase 1 runs
-    const Slot nxt = stream_slot(ws, base + 32 + lane, Ns);
-    if (FUSED && PERM && nxt.idx >= 0)
-      cp_async_i32(ws->pbuf + lane, d.perm + bs->off[nxt.sc & 0xff] + nxt.idx);
+    // this batch's phase space has landed in shared memory (and the permutation entries of the next one)
+    double pfx = 0, pfy = 0, pfz = 0, pfux = 0, pfuy = 0, pfuz = 0, pfid = 0;
+    if (FUSED && cur.idx >= 0) {
+      pfx  = ws->pfb[0][lane];
+      pfy  = ws->pfb[1][lane];
+      pfz  = ws->pfb[2][lane];
+      pfux = ws->pfb[3][lane];
+      pfuy = ws->pfb[4][lane];
+      pfuz = ws->pfb[5][lane];
+      if (PERM)
+        pfid = ws->pfb[6][lane];
+    }
+    // the next batch starts travelling now and has phases 1 and 2 of this one to arrive; the permutation
+    // entries are requested two batches ahead
+    const Slot nn = stream_slot(ws, base + 64 + lane, Ns);
+    if (FUSED) {
+      if (nxt.idx >= 0) {
+        const int64_t off = bs->off[nxt.sc & 0xff];
+        const int64_t i   = PERM ? off + ws->pbuf[lane] : off + nxt.idx;
+#pragma unroll
+        for (int k = 0; k < (PERM ? 7 : 6); k++)
+          cp_async_f64(&ws->pfb[k][lane], d.xu + k * d.pcap + i);
+      }
+      if (PERM && nn.idx >= 0)
+        cp_async_i32(ws->pbuf + lane, d.perm + bs->off[nn.sc & 0xff] + nn.idx);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 
     // ---------------- phase 1: one particle per lane ----------------
     int inf = 0;
@@ -237,7 +291,6 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
       const int64_t i  = bs->off[is] + cur.idx;
       const double  q  = bs->q[is];
       double        x0, y0, z0, x1, y1, z1;
-      double        s0x[3], s0y[3], s0z[3];
       const double  cxf = (double)cx;
       if (FUSED) {
         x0        = pfx;
@@ -249,6 +302,7 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
 
         // weights on the centre grid (MC or WT) and on the edge grid (MC); the particle is in cell
         // (jz, jy, cx) by construction of the sort
+        double s0x[3], s0y[3], s0z[3];
         double wix[3], wiy[3], wiz[3], h[3], whx[4], why[4], whz[4];
         const double dix = (x0 - (xigrid + cxf * dx)) * rdx;
         const double diy = (y0 - yig) * rdy;
@@ -309,9 +363,6 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
         x1 = d.xu[0 * d.pcap + i];
         y1 = d.xu[1 * d.pcap + i];
         z1 = d.xu[2 * d.pcap + i];
-        shape2((x0 - (xigrid + cxf * dx)) * rdx, s0x);
-        shape2((y0 - yig) * rdy, s0y);
-        shape2((z0 - zig) * rdz, s0z);
       }
 
       // new cell: XtensorParticle::count (nix/xtensor_particle.hpp:324-357) and the "after"
@@ -331,7 +382,10 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
           note_leaver(d, seg, i);
       }
 
-      double s1x[3], s1y[3], s1z[3];
+      double s0x[3], s0y[3], s0z[3], s1x[3], s1y[3], s1z[3];
+      shape2((x0 - (xigrid + cxf * dx)) * rdx, s0x);
+      shape2((y0 - yig) * rdy, s0y);
+      shape2((z0 - zig) * rdz, s0z);
       shape2((x1 - (xigrid + (double)ix1 * dx)) * rdx, s1x);
       shape2((y1 - (yigrid + (double)iy1 * dy)) * rdy, s1y);
       shape2((z1 - (zigrid + (double)iz1 * dz)) * rdz, s1z);
@@ -347,83 +401,58 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
       }
     }
     ws->info[lane] = inf;
-    if (FUSED && PERM) {
-      cp_async_commit_wait();
-      __syncwarp();
-    }
-    // the phase space of the next batch is requested before phase 2 of the current one, so its HBM
-    // latency hides behind the accumulation loop
-    if (FUSED && nxt.idx >= 0) {
-      const int64_t off = bs->off[nxt.sc & 0xff];
-      const int64_t i   = PERM ? off + ws->pbuf[lane] : off + nxt.idx;
-      if (PERM)
-        pfid = d.xu[6 * d.pcap + i];
-      pfx  = d.xu[0 * d.pcap + i];
-      pfy  = d.xu[1 * d.pcap + i];
-      pfz  = d.xu[2 * d.pcap + i];
-      pfux = d.xu[3 * d.pcap + i];
-      pfuy = d.xu[4 * d.pcap + i];
-      pfuz = d.xu[5 * d.pcap + i];
-    }
+
+    // ---- the cells of the batch: lanes are in stream order, so the particles of a cell that have the
+    // majority window (the common case) form one ascending lane range, interrupted only by the few
+    // particles with another window and by the idle slot that pads a cell
+    const bool     major = ((inf >> 8) & 0xf) == 0xf;
+    const unsigned mm    = __ballot_sync(FULL, major);
+    const unsigned om    = __ballot_sync(FULL, inf != 0 && !major);
+    unsigned       same  = 0;
+    if (major)
+      same = __match_any_sync(mm, inf);
+    const unsigned leaders = __ballot_sync(FULL, major && (__ffs(same) - 1) == lane);
     __syncwarp();
 
     // ---------------- phase 2: one staged particle per half-warp ----------------
-    // Which passes can take the register-only fast path is decided here once per batch, without
-    // shared-memory loads or votes inside the loop: particle j continues the run of its half-warp
-    // iff it has the majority window and the same info word as its predecessor j-2 (for j < 2: as
-    // the run carried over from the previous batch).  Bit j of `chg` is set otherwise.
-    unsigned chg;
-    {
-      int       pred    = __shfl_up_sync(FULL, inf, 2);
-      const int carried = __shfl_sync(FULL, curinfo, (lane & 1) << 4);
-      if (lane < 2)
-        pred = carried;
-      const bool runs_on = ((inf >> 8) & 0xf) == 0xf && inf == pred;
-      chg                = __ballot_sync(FULL, !runs_on);
-    }
-    const int n     = min(32, total - base);
-    const int npass = (n + 1) >> 1;
-    for (int k = 0; k < npass; k++) {
-      const int     j   = 2 * k + half;
-      const double* rec = ws->stg + j * REC;
-
-      // common case: both particles belong to the cells already being accumulated
-      if (((chg >> (2 * k)) & 3u) == 0u) {
-        accumulate(acc, rec, lm);
-        continue;
-      }
-      const int pinf = ws->info[j];
-
-      const bool valid = (pinf >> 11) & 1;
-      const bool major = valid && ((pinf >> 8) & 7) == 7;
-      const bool minor = valid && !major;
-
-      const bool newcell = major && curinfo != -1 && curinfo != pinf;
-      if (__any_sync(FULL, newcell)) {
+    // Cell by cell (warp-uniform control): when the cell differs from the one the accumulators belong
+    // to, both half-warps add their patches to the tile; then the lane range of the cell is consumed two
+    // records per pass, the lower half-warp the first, the upper one the second.  A record that is not
+    // a majority-window particle of the cell is replaced by the all-zero record.
+    for (unsigned gl = leaders; gl != 0; gl &= gl - 1) {
+      const int      L     = __ffs(gl) - 1;
+      const int      ginfo = __shfl_sync(FULL, inf, L);
+      const unsigned gm    = __shfl_sync(FULL, same, L);
+      const int      last  = 31 - __clz(gm);
+      if (ginfo != curinfo) {
+        if (curinfo != -1) {
 #pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-          if (half == hh && newcell)
-            flush(ws->tile, acc, lm, run_index(curinfo));
-          __syncwarp();
-        }
-        if (newcell)
+          for (int hh = 0; hh < 2; hh++) {
+            if (half == hh)
+              flush(ws->tile, acc, lm, run_index(curinfo));
+            __syncwarp();
+          }
           acc.clear();
+        }
+        curinfo = ginfo;
       }
-      if (major) {
-        curinfo = pinf;
+#pragma unroll 2
+      for (int j = L + half; j <= last + half; j += 2) {
+        const double* rec = ((gm >> (j & 31)) & 1u) && j <= last ? ws->stg + j * REC : ws->zero;
         accumulate(acc, rec, lm);
       }
-      if (__any_sync(FULL, minor)) {
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-          if (half == hh && minor)
-            deposit_direct(ws->tile, rec, lm, run_index(pinf));
-          __syncwarp();
-        }
-      }
     }
+    // the few particles with another window (moved to the lower cell in some direction): straight into
+    // the tile, the whole warp on one record (each half-warp two of the four rows of every patch)
+    for (unsigned mk = om; mk != 0; mk &= mk - 1) {
+      const int j = __ffs(mk) - 1;
+      deposit_direct(ws->tile, ws->stg + j * REC, lm, run_index(ws->info[j]), half);
+    }
+    if (FUSED)
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     cur = nxt;
+    nxt = nn;
   }
 
   // end of the segment: the accumulators of both half-warps
@@ -449,6 +478,22 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
     }
   }
 }
+
+#undef xmin
+#undef ymin
+#undef zmin
+#undef xmax
+#undef ymax
+#undef zmax
+#undef yig
+#undef zig
+#undef yh0
+#undef yh1
+#undef zh0
+#undef zh1
+#undef xigrid
+#undef yigrid
+#undef zigrid
 
 template <bool FUSED>
 int launch_row_kernel(picnix_arena* a, int c0, int cn, double delt)

@@ -65,20 +65,21 @@ constexpr int SY   = XS;
 constexpr int SZ   = 5 * SY + 1;     // 61: odd
 constexpr int TILE = 4 * 5 * SZ;
 
-// staged particle record (doubles): for each window index k = 0..3 a group of five 16-byte pairs,
-// then R.  The order inside a group and the offsets of R are chosen so that no two of the addresses a
-// warp-level load touches (4 components x 2 half-warps, the records of the two half-warps are 54
-// doubles = 6 bank pairs apart) share a bank:
-//   group k at 10 k:  +0 (S0z, DSz)   +2 (S0y, DSy)   +4 (AY, BY)   +6 (S1y, S1y)   +8 (AX, BX)
-//   R at 40:  q S1x[0..3] | Px[0..2], 0 | Py[0..2] | Pz[0..2]      (offsets 0, 4, 8, 11)
-constexpr int REC  = 54;             // 27 x 16 B: odd multiple -> conflict-free 128-bit stores
-constexpr int GRP  = 10;
-constexpr int G_ZA = 0, G_YS = 2, G_YA = 4, G_Y1 = 6, G_XA = 8;
-constexpr int T_R  = 40;
+// staged particle record (doubles): four tables of four 16-byte pairs and R.  The order of the tables and
+// the offsets inside R are chosen so that no two of the addresses a warp-level load touches (4 components
+// x 2 half-warps; the records of the two half-warps are 46 doubles = 14 bank pairs apart) share a bank:
+//    0  ZA[k] = (S0z[k], DSz[k])        8  XA[k] = (AX[k], BX[k])       16  YS[k] = (S0y[k], DSy[k])
+//   24  R: q S1x[0..3] | Px[0..2], 0 | Py[0..2] | Pz[0..2]   (offsets 0, 4, 8, 11)
+//   38  YA[k] = (AY[k], BY[k])
+constexpr int REC  = 46;             // 23 x 16 B: odd multiple -> conflict-free 128-bit stores
+constexpr int T_ZA = 0, T_XA = 8, T_YS = 16, T_R = 24, T_YA = 38;
 
 struct WarpSmem {
   double stg[32 * REC];
   double tile[TILE];
+  double pfb[7][32];                 // phase space of the next batch, filled by cp.async during phases 1 and 2
+  double zero[REC + 2];              // the all-zero record: stands in for a slot that holds no particle of the cell
+  double rowc[16];                   // chunk limits and grid points of the row (see rowpush.cu)
   int    info[32];
   int    pbuf[32];                   // lazy sort: permutation entries of the next batch (cp.async)
   int    pbeg[MAXNS * (RX + 1)];     // [species][cell]: pindex of the row segment's cells
@@ -99,6 +100,11 @@ __device__ __forceinline__ void cp_async_i32(int* smem, const int* gmem)
 {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_f64(double* smem, const double* gmem)
+{
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem)
 {
@@ -201,12 +207,10 @@ __device__ __forceinline__ void stage_particle(double* __restrict__ rec, const A
   const double cx = -q * dxdt, cy = -q * dydt, cz = -q * dzdt;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    double* g = rec + GRP * k;
-    store2(g + G_ZA, fz.S0[k], fz.DS[k]);
-    store2(g + G_YS, fy.S0[k], fy.DS[k]);
-    store2(g + G_YA, fy.S0[k] + A * fy.DS[k], A * fy.S0[k] + B * fy.DS[k]);
-    store2(g + G_Y1, fy.S1[k], fy.S1[k]);
-    store2(g + G_XA, fx.S0[k] + A * fx.DS[k], A * fx.S0[k] + B * fx.DS[k]);
+    store2(rec + T_ZA + 2 * k, fz.S0[k], fz.DS[k]);
+    store2(rec + T_XA + 2 * k, fx.S0[k] + A * fx.DS[k], A * fx.S0[k] + B * fx.DS[k]);
+    store2(rec + T_YS + 2 * k, fy.S0[k], fy.DS[k]);
+    store2(rec + T_YA + 2 * k, fy.S0[k] + A * fy.DS[k], A * fy.S0[k] + B * fy.DS[k]);
   }
   const double px0 = fx.DS[0], px1 = px0 + fx.DS[1], px2 = px1 + fx.DS[2];
   const double py0 = fy.DS[0], py1 = py0 + fy.DS[1], py2 = py1 + fy.DS[2];
@@ -225,7 +229,8 @@ struct LaneMap {
   int pq;   // record offset of (P, Q)
   int uv;   // record offset of the (U[i], V[i]) table
   int r;    // record offset of R[0..3] (the currents have three prefix values; their R[3] is whatever
-            // follows -- for Jz the first word behind the record -- and feeds a column that is never flushed)
+            // follows and feeds a column that is never flushed)
+  double e; // 1 for rho, 0 for the currents: (P, Q) <- (P + e Q, Q + e P) turns (S0z, DSz) into (S1z, S1z)
   int lin;  // lane part of the tile index (the run adds wz*SZ + wy*SY + jx + wx)
   int si;   // tile stride of i, in elements (already x 4 components)
   int sj;   // tile stride of j
@@ -238,8 +243,9 @@ __device__ __forceinline__ LaneMap lane_map(int lane)
   const int c = (lane >> 2) & 3;
   LaneMap   m;
   m.c   = c;
-  m.pq  = (c == 3 ? G_XA : G_ZA) + GRP * a;
-  m.uv  = c == 0 ? G_Y1 : (c == 1 ? G_YA : (c == 2 ? G_XA : G_YS));
+  m.pq  = (c == 3 ? T_XA : T_ZA) + 2 * a;
+  m.uv  = c == 1 ? T_YA : (c == 2 ? T_XA : T_YS);
+  m.e   = c == 0 ? 1.0 : 0.0;
   m.r   = T_R + (c == 0 ? 0 : (c == 1 ? 4 : (c == 2 ? 8 : 11)));
   m.lin = c == 0 ? a * SZ : (c == 1 ? a * SZ + 1 : (c == 2 ? a * SZ + SY : SZ + a));
   m.si  = 4 * (c == 2 ? 1 : SY);
@@ -264,15 +270,17 @@ struct Operands {
   double w[4], r[4];
 };
 
-// the factors of one staged particle as seen by lane (c, a): 5 16-byte + 4 8-byte shared loads
+// the factors of one staged particle as seen by lane (c, a): 5 16-byte + 4 8-byte shared loads.
+//   rho: w[i] = S0y[i] S1z[a] + DSy[i] S1z[a] = S1y[i] S1z[a]      (P, Q) = (S0z, DSz)[a] -> (S1z, S1z)[a]
 __device__ __forceinline__ Operands load_operands(const double* __restrict__ rec, const LaneMap& m)
 {
   Operands      o;
   const double2 pq = *reinterpret_cast<const double2*>(rec + m.pq);
+  const double  P = pq.x + m.e * pq.y, Q = pq.y + m.e * pq.x;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    const double2 uv = *reinterpret_cast<const double2*>(rec + m.uv + GRP * i);
-    o.w[i]           = uv.x * pq.x + uv.y * pq.y;
+    const double2 uv = *reinterpret_cast<const double2*>(rec + m.uv + 2 * i);
+    o.w[i]           = uv.x * P + uv.y * Q;
   }
 #pragma unroll
   for (int j = 0; j < 4; j++)
@@ -306,20 +314,28 @@ __device__ __forceinline__ void flush(double* __restrict__ tile, const Acc& acc,
   }
 }
 
-// one staged particle straight into the warp tile (no register accumulators): the few particles
-// whose window differs from the run being accumulated
+// one staged particle straight into the warp tile (no register accumulators), the whole warp on it:
+// half-warp h adds rows i = 2h, 2h+1 of every lane's patch.  For the few particles whose window
+// differs from the run being accumulated.
 __device__ __forceinline__ void deposit_direct(double* __restrict__ tile, const double* __restrict__ rec,
-                                               const LaneMap& m, int run)
+                                               const LaneMap& m, int run, int half)
 {
-  const Operands o = load_operands(rec, m);
-  double*        p = tile + 4 * (m.lin + run) + m.c;
+  const double2 pq = *reinterpret_cast<const double2*>(rec + m.pq);
+  const double  P = pq.x + m.e * pq.y, Q = pq.y + m.e * pq.x;
+  double        r[4];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
+  for (int j = 0; j < 4; j++)
+    r[j] = rec[m.r + j];
+  double* p = tile + 4 * (m.lin + run) + m.c + 2 * half * m.si;
+#pragma unroll
+  for (int ii = 0; ii < 2; ii++) {
+    const double2 uv = *reinterpret_cast<const double2*>(rec + m.uv + 2 * (2 * half + ii));
+    const double  w  = uv.x * P + uv.y * Q;
 #pragma unroll
     for (int j = 0; j < 3; j++)
-      p[i * m.si + j * m.sj] += o.w[i] * o.r[j];
+      p[ii * m.si + j * m.sj] += w * r[j];
     if (m.c == 0)
-      p[i * m.si + 3 * m.sj] += o.w[i] * o.r[3];
+      p[ii * m.si + 3 * m.sj] += w * r[3];
   }
 }
 

@@ -1,0 +1,148 @@
+"""The drop-in, actually dropped in: the reference's OWN application
+(nix::Application::main -> PicApplication::push_openmp -> example/thermal MainChunk, config.toml
+driven) is run twice with the same configuration file
+
+  * host/ref_binding/_build/thermal_ref   -- unmodified, PicChunk on the host CPU
+  * host/ref_binding/_build/thermal_cuda  -- the same main.cpp with MainChunk deriving from
+    CudaPicChunk (host/ref_binding/cuda_pic_chunk.hpp), i.e. every kernel of the step on the B200
+    through the C ABI, history / field / particle diagnostics written by the reference's own writers
+
+and the outputs are compared: history.txt (div errors, field and particle energies; the file holds 7
+significant digits), the raw field dumps (uf and the moments um, full precision) and the raw particle
+dumps (matched by particle id).  Both binaries are built by host/ref_binding/Makefile in the container
+that has the reference tree and travel to the GPU box; the test skips when they are absent.
+"""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "host", "ref_binding", "_build")
+REF, CUDA = os.path.join(BUILD, "thermal_ref"), os.path.join(BUILD, "thermal_cuda")
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(CUDA)),
+                                 reason="host/ref_binding/_build is not built (needs the reference tree)")]
+
+CONFIG = """
+[application]
+  basedir = 'data'
+  [application.log]
+    interval = 100
+  [application.rebalance]
+    interval = 1000000
+  [application.option]
+    vectorization = 'vector'
+    seed_type = 'fixed'
+    order = {order}
+
+[[diagnostic]]
+  name = 'history'
+  interval = 1
+
+[[diagnostic]]
+  name = 'field'
+  interval = {nstep}
+
+[[diagnostic]]
+  name = 'particle'
+  interval = {nstep}
+  fraction = 1.0
+
+[parameter]
+  Nx = {nx}
+  Ny = {ny}
+  Nz = {nz}
+  Cx = {cx}
+  Cy = {cy}
+  Cz = {cz}
+  Ex = 0.0
+  Ey = 0.0
+  Ez = 0.0
+  Bx = 5.0
+  By = 0.0
+  Bz = 0.0
+  Ns = 2
+  cc = 10.0
+  delt = 0.05
+  delh = 1.0
+
+[[parameter.particle]]
+    np = {ppc}
+    qm = -1.0
+    ro = 1.0
+    vt = 1.0
+
+[[parameter.particle]]
+    np = {ppc}
+    qm = +0.1
+    ro = 10.0
+    vt = 0.31622776601
+"""
+
+
+def run_app(binary, workdir, cfg, nstep):
+    os.makedirs(workdir, exist_ok=True)
+    with open(os.path.join(workdir, "config.toml"), "w") as fp:
+        fp.write(cfg)
+    env = dict(os.environ, OMP_NUM_THREADS="4", PICNIX_SYNC_HOST_INTERVAL="1")
+    proc = subprocess.run([binary, "-c", "config.toml", "-t", str(0.05 * nstep)], cwd=workdir, env=env,
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-3000:]
+    return os.path.join(workdir, "data")
+
+
+def read_history(path):
+    rows = [line.split() for line in open(os.path.join(path, "history.txt")) if not line.startswith("#")]
+    return np.array([[float(v) for v in r] for r in rows])
+
+
+def read_dump(path, kind, step):
+    meta = json.load(open(os.path.join(path, kind, f"{step:08d}.json")))
+    raw = np.fromfile(os.path.join(path, kind, meta["meta"]["rawfile"]), dtype=np.uint8)
+    out = {}
+    for name, ds in meta["dataset"].items():
+        if ds["datatype"] != "f8":
+            continue
+        out[name] = raw[ds["offset"]:ds["offset"] + ds["size"]].view(np.float64).reshape(ds["shape"])
+    return out
+
+
+@pytest.mark.parametrize("shape", ["3d", "2d"])
+def test_reference_application_with_cuda_chunks(tmp_path, shape):
+    nstep = 20
+    geom = dict(nx=16, ny=16, nz=16, cx=2, cy=2, cz=2, ppc=8) if shape == "3d" else \
+        dict(nx=32, ny=32, nz=1, cx=4, cy=2, cz=1, ppc=16)
+    cfg = CONFIG.format(order=2, nstep=nstep, **geom)
+    ref = run_app(REF, str(tmp_path / "ref"), cfg, nstep)
+    gpu = run_app(CUDA, str(tmp_path / "gpu"), cfg, nstep)
+
+    # history.txt: step, time, div(E), div(B), E^2/2, B^2/2, particle energies (%13.6e each)
+    ha, hb = read_history(gpu), read_history(ref)
+    assert ha.shape == hb.shape and ha.shape[0] >= nstep + 1
+    assert np.array_equal(ha[:, :2], hb[:, :2])
+    assert np.max(np.abs(ha[:, 2:4])) < 1e-10 and np.max(np.abs(hb[:, 2:4])) < 1e-10  # round-off on both sides
+    scale = np.maximum(np.abs(hb[:, 4:]), 1e-300)
+    assert np.max(np.abs(ha[:, 4:] - hb[:, 4:]) / scale) < 3e-6  # the printed precision
+
+    # full precision: raw field dump of the last step (uf interior and moments um of every chunk)
+    fa, fb = read_dump(gpu, "field", nstep), read_dump(ref, "field", nstep)
+    assert set(fa) == set(fb) and "uf" in fa
+    for name in fa:
+        assert fa[name].shape == fb[name].shape
+        assert np.max(np.abs(fa[name] - fb[name])) <= 1e-10 * np.max(np.abs(fb[name])), name
+
+    # raw particle dump, matched by the 64-bit id stored in component 6
+    pa, pb = read_dump(gpu, "particle", nstep), read_dump(ref, "particle", nstep)
+    assert set(pa) == set(pb) and len(pa) >= 2
+    for name in pa:
+        a, b = pa[name].reshape(-1, 7), pb[name].reshape(-1, 7)
+        assert a.shape == b.shape
+        a = a[np.argsort(a[:, 6].view(np.int64), kind="stable")]
+        b = b[np.argsort(b[:, 6].view(np.int64), kind="stable")]
+        assert np.array_equal(a[:, 6].view(np.int64), b[:, 6].view(np.int64))
+        assert np.max(np.abs(a[:, :3] - b[:, :3])) < 1e-11 * 32
+        assert np.max(np.abs(a[:, 3:6] - b[:, 3:6])) < 1e-11 * 10

@@ -86,11 +86,22 @@ def main():
     if locs is None:
         print("no matching SASS section found in", obj)
         return
-    agg = defaultdict(lambda: [0, 0])
+    agg = defaultdict(lambda: [0, 0, 0, 0])
+    iW = h.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in h else None
+    iWi = h.index("L1 Wavefronts Shared Ideal") if "L1 Wavefronts Shared Ideal" in h else None
     for loc, r in zip(locs, data):
         k = loc or ("?", 0)
         agg[k][0] += int(r[iS])
         agg[k][1] += int(r[iI])
+        if iW is not None:
+            agg[k][2] += int(r[iW] or 0)
+            agg[k][3] += int(r[iWi] or 0)
+    tw = sum(v[2] for v in agg.values())
+    if tw:
+        print(f"\nshared-memory wavefronts {tw} (ideal {sum(v[3] for v in agg.values())}); by source line (% of all, "
+              f"wavefronts per warp instruction):")
+        for (f, l), v in sorted(agg.items(), key=lambda kv: -kv[1][2])[:14]:
+            print(f"  {f}:{l:4d} {100 * v[2] / tw:5.1f}%  ideal {100 * v[3] / tw:5.1f}%")
     srcdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "picnix_b200", "csrc")
     cache = {}
     print("\nhottest source lines (samples % / executed %):")
