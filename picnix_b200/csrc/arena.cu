@@ -414,6 +414,14 @@ int picnix_cuda_arena_create(const picnix_config_t* cfg, const int32_t* boundary
     return status;
   if ((status = dev_alloc(a, &a->d_reduce, (size_t)g.nchunk * 4)) != PICNIX_OK)
     return status;
+  if ((status = dev_alloc(a, &a->d.seg_stat, 4)) != PICNIX_OK)
+    return status;
+  if ((status = dev_alloc(a, &a->d.spill_count, 1)) != PICNIX_OK)
+    return status;
+  PICNIX_CUDA(a, cudaMallocHost((void**)&a->h_stat, 4 * sizeof(int)));
+  PICNIX_CUDA(a, cudaEventCreateWithFlags(&a->stat_event, cudaEventDisableTiming));
+  if (const char* env = std::getenv("PICNIX_CHECK_GROWTH"))
+    a->check_growth_always = std::atoi(env) != 0;
   a->d.far_cap = 1 << 18;
   if ((status = dev_alloc(a, &a->d.far_count, 1)) != PICNIX_OK)
     return status;
@@ -468,6 +476,13 @@ int picnix_cuda_arena_destroy(picnix_arena_t* a)
   dev_free(a->d.far_rec);
   dev_free(a->d.leave_count);
   dev_free(a->d.leave_idx);
+  dev_free(a->d.spill_count);
+  dev_free(a->d.spill_rec);
+  dev_free(a->d.seg_stat);
+  if (a->h_stat)
+    cudaFreeHost(a->h_stat);
+  if (a->stat_event)
+    cudaEventDestroy(a->stat_event);
   dev_free(a->d_reduce);
   hostio_destroy(a);
   dev_free(a->d_stage);
@@ -532,7 +547,8 @@ int picnix_cuda_synchronize(picnix_arena_t* a)
   int flags[4];
   PICNIX_CUDA(a, cudaMemcpy(flags, a->d.errflag, sizeof(flags), cudaMemcpyDeviceToHost));
   if (flags[0] != 0)
-    return fail(a, PICNIX_ERR_OVERFLOW, "particle segment overflow (increase buffer_ratio)");
+    return fail(a, PICNIX_ERR_OVERFLOW,
+                "particle spill list overflow: more migrants than segments and spill list can hold in one step");
   if (flags[1] != 0)
     return fail(a, PICNIX_ERR_OVERFLOW, "particle migration send buffer overflow");
   if (flags[2] != 0)
@@ -599,8 +615,11 @@ int picnix_cuda_set_particle_capacity(picnix_arena_t* a, const int32_t* np_alloc
   dev_free(a->d.perm);
   dev_free(a->d.leave_count);
   dev_free(a->d.leave_idx);
+  dev_free(a->d.spill_rec);
   a->leave_list_valid = false;
   a->perm_pending     = false;
+  a->stat_known       = false;
+  a->stat_pending     = false;
 
   int64_t total = 0;
   for (int s = 0; s < a->nseg; s++) {
@@ -630,6 +649,21 @@ int picnix_cuda_set_particle_capacity(picnix_arena_t* a, const int32_t* np_alloc
     return status;
   if ((status = dev_alloc(a, &a->d.leave_idx, (size_t)a->d.leave_cap, false)) != PICNIX_OK)
     return status;
+  // migrants that do not fit wait here until their segment has grown (grow.cu); the list of particles
+  // that moved more than a cell (rowpush.cu) scales with the population as well
+  a->d.spill_cap = (int)std::min<int64_t>(std::max<int64_t>(65536, total / 16), 1 << 28);
+  if ((status = dev_alloc(a, &a->d.spill_rec, (size_t)a->d.spill_cap * 8, false)) != PICNIX_OK)
+    return status;
+  PICNIX_CUDA(a, cudaMemset(a->d.spill_count, 0, sizeof(int)));
+  {
+    const int want = (int)std::min<int64_t>(std::max<int64_t>(1 << 18, total / 16), 1 << 28);
+    if (want > a->d.far_cap) {
+      dev_free(a->d.far_rec);
+      a->d.far_cap = want;
+      if ((status = dev_alloc(a, &a->d.far_rec, (size_t)want * 8, false)) != PICNIX_OK)
+        return status;
+    }
+  }
   PICNIX_CUDA(a, cudaMemcpy(a->d.seg_off, a->seg_off.data(), a->nseg * sizeof(int64_t),
                             cudaMemcpyHostToDevice));
   PICNIX_CUDA(a, cudaMemcpy(a->d.seg_cap, a->seg_cap.data(), a->nseg * sizeof(int32_t),

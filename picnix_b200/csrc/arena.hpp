@@ -80,6 +80,12 @@ struct DevPtrs {
   int*     leave_count; // [1]
   int64_t* leave_idx;   // [leave_cap]
   int      leave_cap;
+  // migrants that found their destination full (a segment, or a peer's message bound): kept here
+  // instead of being dropped and re-appended after the segments have grown (grow.cu)
+  int*     spill_count; // [1]
+  double*  spill_rec;   // [spill_cap][8] 7 components + tag (int2: destination segment | ~message slot, species)
+  int      spill_cap;
+  int*     seg_stat;    // [4] min over segments of (capacity - np), max ntail, spill count, -- ; written by the sort
 };
 
 struct PeerPlan {
@@ -162,6 +168,15 @@ struct picnix_arena {
   bool                   force_generic = false; // testing: bypass the tiled kernels
   bool                   deposit_mma   = false; // row kernel variant: deposit through the FP64 MMA unit
   int                    row_version   = 2;     // option "row_kernel": 2 = rowpush.cu, 1 = round-1 kernel (rowfused.cu)
+  // growth of particle segments (grow.cu): statistics of the previous step arrive one step late
+  int*                   h_stat       = nullptr; // pinned [4] copy of DevPtrs::seg_stat
+  cudaEvent_t            stat_event   = nullptr;
+  bool                   stat_pending = false;
+  bool                   stat_known   = false;
+  int                    stat_minfree = 0, stat_maxtail = 0, stat_spilled = 0;
+  bool                   check_growth_always = false; // option "check_growth": host check before every sort
+  int64_t                segment_regrows = 0;   // how often the particle arrays were re-laid out
+  int64_t                late_particles  = 0;   // migrants delivered one step late (spilled in the unchecked path)
   int64_t                kernel_launches = 0;
   int64_t                particle_pushes = 0;
   int64_t                np_total_hint   = 0; // sum of np at last host-visible count
@@ -219,6 +234,8 @@ int launch_count(picnix_arena* a, int c0, int cn);
 int launch_sort(picnix_arena* a, int c0, int cn);
 int materialize_sort(picnix_arena* a); // physically order xu if an index-only sort is pending
 
+int resolve_growth(picnix_arena* a);  // grow.cu: before the sort of the particle exchange
+int record_segment_stats(picnix_arena* a);
 int launch_halo_begin(picnix_arena* a, int mode);
 int launch_halo_end(picnix_arena* a, int mode);
 

@@ -232,6 +232,25 @@ struct MigrateTables {
   const int* nbid;       // [nchunk][27] global neighbour ids (for remote records)
 };
 
+// A migrant whose destination is full -- a segment, or the bounded message to a peer -- is kept in the
+// spill list instead of being dropped: tag.x >= 0 is the destination segment (re-appended by grow.cu once
+// the segment has grown), tag.x < 0 is ~(message slot) of a remote neighbour (re-sent with the next
+// exchange).  Only a full spill list loses particles, and that is an error.
+__device__ __forceinline__ void spill_particle(const DevPtrs& d, const double* p, int dest, int tagy)
+{
+  const int k = atomicAdd(d.spill_count, 1);
+  if (k >= d.spill_cap) {
+    atomicExch(d.errflag + 0, 1);
+    return;
+  }
+  double* out = d.spill_rec + (int64_t)k * 8;
+#pragma unroll
+  for (int c = 0; c < NC; c++)
+    out[c] = p[c];
+  int2 tag = make_int2(dest, tagy);
+  out[7]   = *reinterpret_cast<double*>(&tag);
+}
+
 // append one particle behind the active particles of (chunk, species); p = 7 components
 __device__ __forceinline__ void append_particle(const Geom& g, const DevPtrs& d, int chunk, int is,
                                                 double* p)
@@ -240,7 +259,10 @@ __device__ __forceinline__ void append_particle(const Geom& g, const DevPtrs& d,
   const int slot = atomicAdd(d.ntail + seg, 1);
   const int ip   = d.np[seg] + slot;
   if (ip >= d.seg_cap[seg]) {
-    atomicExch(d.errflag + 0, 1);
+    // XtensorHaloParticle3D::pre_unpack would have resized first (nix/xtensor_halo3d.hpp:406-418): wait
+    // in the spill list for resolve_growth()
+    atomicSub(d.ntail + seg, 1);
+    spill_particle(d, p, seg, is);
     return;
   }
   // post_unpack: periodic wrap, then count in the receiving chunk's geometry
@@ -276,7 +298,10 @@ __device__ __forceinline__ void migrate_particle(const Geom& g, const DevPtrs& d
     const int     peer = tab.slot_peer[slot];
     const int     rec  = atomicAdd(tab.psend_cnt[peer], 1);
     if (rec >= tab.psend_cap[peer]) {
-      atomicExch(d.errflag + 1, 1);
+      // the message to this peer is full (lagged-count bound): send it with the next exchange
+      atomicSub(tab.psend_cnt[peer], 1);
+      spill_particle(d, p, ~slot, tab.nbid[chunk * NBSIZE + dir] | (is << 24));
+      atomicExch(d.errflag + 1, 1); // reported as late delivery, not as an error
       return;
     }
     double* out = tab.psend[peer] + (int64_t)rec * 8;

@@ -75,26 +75,22 @@ struct Slot {
   int idx, sc;
 };
 
-__device__ __forceinline__ Slot stream_slot(const WarpSmem* ws, int t, int Ns)
+// slot t of the stream; k is the lane's cursor into the entry table (slots are asked for in
+// ascending order, an entry is about one batch long: the loop runs once or twice)
+__device__ __forceinline__ Slot stream_slot(const WarpSmem* ws, int t, int nent, int& k)
 {
+  while (k < nent && t >= ws->ent[k + 1].x)
+    k++;
   Slot s;
   s.idx = -1;
   s.sc  = 0;
-  if (t >= ws->poff[RX])
-    return s;
-  int c = 0;
-#pragma unroll
-  for (int k = 1; k < RX; k++)
-    c += t >= ws->poff[k];
-  int rem = t - ws->poff[c];
-  for (int is = 0; is < Ns; is++) {
-    const int b = ws->pbeg[is * (RX + 1) + c];
-    const int n = ws->pbeg[is * (RX + 1) + c + 1] - b;
-    if (rem >= 0 && rem < n) {
-      s.idx = b + rem;
-      s.sc  = is | (c << 8);
+  if (k < nent) {
+    const int4 e = ws->ent[k];
+    const int  r = t - e.x;
+    if (r < e.z) {
+      s.idx = e.y + r;
+      s.sc  = e.w;
     }
-    rem -= n; // negative once a species has taken the slot: no later species matches
   }
   return s;
 }
@@ -157,28 +153,43 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
     bs->off[is]     = d.seg_off[chunk * Ns + is];
   }
 
-  // ---- the stream of this warp's row segment: cell boundaries of every species, padded cell offsets ----
+  // ---- the stream of this warp's row segment: lane (cell c, species is) = c * Ns + is builds its entry;
+  // cells are padded to a multiple of ALIGN slots ----
   const int key0 = jz * g.fsz + jy * g.fsy + jx0;
+  const int nent = RX * Ns;
   {
-    int cnt = 0;
-    for (int is = 0; is < Ns; is++) {
-      const int* pix = d.pindex + (int64_t)(chunk * Ns + is) * (g.Ng + 1);
-      const int  v   = lane <= RX ? pix[key0 + lane] : 0;
-      if (lane <= RX)
-        ws->pbeg[is * (RX + 1) + lane] = v;
-      const int nxt = __shfl_down_sync(FULL, v, 1);
-      cnt += lane < RX ? nxt - v : 0;
+    const int c  = lane / Ns;
+    const int is = lane - c * Ns;
+    int       b = 0, n = 0;
+    if (lane < nent) {
+      const int* pix = d.pindex + (int64_t)(chunk * Ns + is) * (g.Ng + 1) + key0 + c;
+      b              = pix[0];
+      n              = pix[1] - b;
     }
-    const int padded = (cnt + ALIGN - 1) & ~(ALIGN - 1);
-    int       incl   = padded;
+    // exclusive prefix of the counts over the lanes
+    int incl = n;
 #pragma unroll
-    for (int dd = 1; dd <= RX; dd <<= 1) {
+    for (int dd = 1; dd < 32; dd <<= 1) {
       const int t = __shfl_up_sync(FULL, incl, dd);
       if (lane >= dd)
         incl += t;
     }
-    if (lane <= RX)
-      ws->poff[lane] = incl - padded; // lane RX: the length of the stream
+    // padding accumulated before cell c: every earlier cell rounds its total up to ALIGN
+    const int cellend = __shfl_sync(FULL, incl, min(c * Ns + Ns - 1, 31)); // slots of cells 0..c
+    const int celltot = cellend - __shfl_sync(FULL, incl - n, min(c * Ns, 31));
+    int       pad     = (lane < nent && is == Ns - 1) ? ((celltot + ALIGN - 1) & ~(ALIGN - 1)) - celltot : 0;
+    int       pincl   = pad;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const int t = __shfl_up_sync(FULL, pincl, dd);
+      if (lane >= dd)
+        pincl += t;
+    }
+    const int start = (incl - n) + (pincl - pad); // unpadded start + padding of the cells before
+    if (lane < nent)
+      ws->ent[lane] = make_int4(start, b, n, is | (c << 8));
+    if (lane == nent - 1)
+      ws->ent[nent] = make_int4(start + n + pad, 0, 0, 0);
   }
   for (int i = lane; i < TILE; i += 32)
     ws->tile[i] = 0.0;
@@ -186,12 +197,13 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
     ws->zero[i] = 0.0;
   __syncthreads(); // stream tables and species constants visible (the field tile is still in flight)
 
-  const int total = ws->poff[RX];
+  const int total = ws->ent[nent].x;
 
   // ---- first batch: its phase space travels global -> shared behind the field tile; so do the
   // permutation entries of the second batch (everything asynchronous, nothing held in registers) ----
-  Slot cur = stream_slot(ws, lane, Ns);
-  Slot nxt = stream_slot(ws, 32 + lane, Ns);
+  int  kent = 0;
+  Slot cur  = stream_slot(ws, lane, nent, kent);
+  Slot nxt  = stream_slot(ws, 32 + lane, nent, kent);
   if (FUSED) {
     if (cur.idx >= 0) {
       const int64_t off = bs->off[cur.sc & 0xff];
@@ -268,7 +280,7 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
     }
     // the next batch starts travelling now and has phases 1 and 2 of this one to arrive; the permutation
     // entries are requested two batches ahead
-    const Slot nn = stream_slot(ws, base + 64 + lane, Ns);
+    const Slot nn = stream_slot(ws, base + 64 + lane, nent, kent);
     if (FUSED) {
       if (nxt.idx >= 0) {
         const int64_t off = bs->off[nxt.sc & 0xff];
@@ -342,11 +354,14 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
         double by = interp_cell<4, 3, 4>(F + 4, whz, wiy, whx) * qmdt;
         double bz = interp_cell<3, 4, 4>(F + 5, wiz, why, whx) * qmdt;
 
-        push_momentum<Pusher>(ux, uy, uz, ex, ey, ez, bx, by, bz, rc.cc);
+        if (Pusher == PICNIX_PUSHER_BORIS)
+          push_boris_fast(ux, uy, uz, ex, ey, ez, bx, by, bz, rc.cc);
+        else
+          push_momentum<Pusher>(ux, uy, uz, ex, ey, ez, bx, by, bz, rc.cc);
         x1 = x0;
         y1 = y0;
         z1 = z0;
-        push_position(x1, y1, z1, ux, uy, uz, rc.rc, delt);
+        push_position_fast(x1, y1, z1, ux, uy, uz, rc.rc, delt);
         double* xo = PERM ? d.xv : d.xu; // i is the SORTED slot: in place, or the other buffer
         xo[0 * d.pcap + i] = x1;
         xo[1 * d.pcap + i] = y1;
@@ -426,20 +441,29 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
       const int      last  = 31 - __clz(gm);
       if (ginfo != curinfo) {
         if (curinfo != -1) {
-#pragma unroll
-          for (int hh = 0; hh < 2; hh++) {
-            if (half == hh)
-              flush(ws->tile, acc, lm, run_index(curinfo));
-            __syncwarp();
-          }
+          flush(ws->tile, acc, lm, run_index(curinfo), half);
+          __syncwarp();
           acc.clear();
         }
         curinfo = ginfo;
       }
+      const int cnt = last - L + 1;
+      if (__popc(gm) == cnt) {
+        // no foreign slot inside the range (the usual case): plain pointer walk
+        const double* rec = ws->stg + (L + half) * REC;
 #pragma unroll 2
-      for (int j = L + half; j <= last + half; j += 2) {
-        const double* rec = ((gm >> (j & 31)) & 1u) && j <= last ? ws->stg + j * REC : ws->zero;
-        accumulate(acc, rec, lm);
+        for (int k = 0; k < (cnt >> 1); k++) {
+          accumulate(acc, rec, lm);
+          rec += 2 * REC;
+        }
+        if (cnt & 1)
+          accumulate(acc, half == 0 ? rec : ws->zero, lm);
+      } else {
+#pragma unroll 1
+        for (int j = L + half; j <= last + half; j += 2) {
+          const double* rec = ((gm >> (j & 31)) & 1u) && j <= last ? ws->stg + j * REC : ws->zero;
+          accumulate(acc, rec, lm);
+        }
       }
     }
     // the few particles with another window (moved to the lower cell in some direction): straight into
@@ -456,12 +480,9 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
   }
 
   // end of the segment: the accumulators of both half-warps
-#pragma unroll
-  for (int hh = 0; hh < 2; hh++) {
-    if (half == hh && curinfo != -1)
-      flush(ws->tile, acc, lm, run_index(curinfo));
-    __syncwarp();
-  }
+  if (curinfo != -1)
+    flush(ws->tile, acc, lm, run_index(curinfo), half);
+  __syncwarp();
 
   // warp tile -> global current: one fp64 reduction per non-zero tile value; tile and uj both keep
   // the four components of a point together, so a (z, y) line of the tile is one contiguous run of uj

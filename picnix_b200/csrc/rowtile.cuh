@@ -43,7 +43,7 @@ namespace rowtile
 constexpr int RX      = 8;           // cells per row segment
 constexpr int WARPS   = 4;           // rows (consecutive y) per block
 constexpr int THREADS = WARPS * 32;
-constexpr int MAXNS   = 8;           // species the merged stream can hold
+constexpr int MAXNS   = 4;           // species the merged stream can hold
 constexpr int ALIGN   = 2;           // every cell starts at a multiple of ALIGN slots of the stream
 
 // field tile: points x in [jx0-1, jx0+RX+1], y in [jy0-1, jy0+WARPS+1], z in [jz-1, jz+2],
@@ -82,8 +82,10 @@ struct WarpSmem {
   double rowc[16];                   // chunk limits and grid points of the row (see rowpush.cu)
   int    info[32];
   int    pbuf[32];                   // lazy sort: permutation entries of the next batch (cp.async)
-  int    pbeg[MAXNS * (RX + 1)];     // [species][cell]: pindex of the row segment's cells
-  int    poff[RX + 4];               // first stream slot of each cell; [RX] = length of the stream
+  // the merged stream of the row segment: entry k = cell * Ns + species covers the stream slots
+  // [ent[k].x, ent[k].x + ent[k].z) with the particles ent[k].y, ent[k].y + 1, ... of that species' segment;
+  // .w = species | cell << 8; ent[RX * Ns].x = length of the stream (cells padded to ALIGN slots)
+  int4   ent[MAXNS * RX + 1];
 };
 
 struct BlockSmem {
@@ -132,6 +134,48 @@ __device__ __forceinline__ void shape2(double delta, double* s)
   s[0] = 0.50 * w1 * w1;
   s[1] = 0.75 - delta * delta;
   s[2] = 0.50 * w2 * w2;
+}
+
+// 1 / x for finite x >= 1 without the special-case branches of the IEEE division: hardware
+// approximation + two Newton steps (relative error about one ulp; the parity bar on momenta is 1e-13)
+__device__ __forceinline__ double rcp_fast(double x)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+
+// Boris push (nix/primitives.hpp:164-189) with the reciprocal square root and the reciprocal taken
+// directly instead of through sqrt + two divisions; e* and b* are already multiplied by (q/m) dt / 2
+__device__ __forceinline__ void push_boris_fast(double& ux, double& uy, double& uz, double ex, double ey,
+                                                double ez, double bx, double by, double bz, double cc)
+{
+  ux += ex;
+  uy += ey;
+  uz += ez;
+  const double gm = rsqrt(cc * cc + ux * ux + uy * uy + uz * uz);
+  bx *= gm;
+  by *= gm;
+  bz *= gm;
+  const double bb = 2.0 * rcp_fast(1.0 + bx * bx + by * by + bz * bz);
+  const double vx = ux + (uy * bz - uz * by);
+  const double vy = uy + (uz * bx - ux * bz);
+  const double vz = uz + (ux * by - uy * bx);
+  ux += (vy * bz - vz * by) * bb + ex;
+  uy += (vz * bx - vx * bz) * bb + ey;
+  uz += (vx * by - vy * bx) * bb + ez;
+}
+
+// position update (pic/engine/position.hpp:117-130): x += u dt / gamma
+__device__ __forceinline__ void push_position_fast(double& x, double& y, double& z, double ux, double uy,
+                                                   double uz, double rc, double delt)
+{
+  const double dt = delt * rsqrt(1 + (ux * ux + uy * uy + uz * uz) * rc * rc);
+  x += ux * dt;
+  y += uy * dt;
+  z += uz * dt;
 }
 
 // the three weights of the edge grid in the cell-anchored 4-slot array: slot k <-> edge cell-1+k;
@@ -299,18 +343,24 @@ __device__ __forceinline__ void accumulate(Acc& acc, const double* __restrict__ 
       acc.v[i][j] += o.w[i] * o.r[j];
 }
 
-// add a lane's patch into the warp tile; run = wz*SZ + wy*SY + jx + wx of the cell and window the
-// accumulators belong to.  The current components only have three prefix values (j < 3).
-__device__ __forceinline__ void flush(double* __restrict__ tile, const Acc& acc, const LaneMap& m, int run)
+// Both half-warps hold a patch of the SAME cell and window (run = wz*SZ + wy*SY + jx + wx).  They first
+// add the two patches lane-wise -- each half keeps two of the four rows i and receives the partner's
+// contribution to them by shuffle -- and then every lane adds its two rows into the warp tile: all 32
+// lanes busy, no serialisation of the halves.  The current components only have three prefix values (j < 3).
+__device__ __forceinline__ void flush(double* __restrict__ tile, const Acc& acc, const LaneMap& m, int run,
+                                      int half)
 {
-  double* p = tile + 4 * (m.lin + run) + m.c;
+  double* p = tile + 4 * (m.lin + run) + m.c + 2 * half * m.si;
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
+  for (int ii = 0; ii < 2; ii++) {
 #pragma unroll
-    for (int j = 0; j < 3; j++)
-      p[i * m.si + j * m.sj] += acc.v[i][j];
-    if (m.c == 0)
-      p[i * m.si + 3 * m.sj] += acc.v[i][3];
+    for (int j = 0; j < 4; j++) {
+      const double give = half ? acc.v[ii][j] : acc.v[2 + ii][j];     // the partner's row
+      const double keep = half ? acc.v[2 + ii][j] : acc.v[ii][j];     // row i = 2 * half + ii
+      const double sum  = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+      if (j < 3 || m.c == 0)
+        p[ii * m.si + j * m.sj] += sum;
+    }
   }
 }
 
