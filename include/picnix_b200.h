@@ -113,6 +113,10 @@ const char* picnix_cuda_last_error(const picnix_arena_t* arena);
  *                        fused kernel will consume the result only the permutation is written and
  *                        the reordering rides on the next push; results are identical)
  *   "deposit_mma"   = 1  FP64-MMA formulation of the deposit (slower; kept as measured evidence)
+ *   "row_kernel"    = 1  the round-1 tiled kernel (rowfused.cu) instead of rowpush.cu (default 2)
+ *   "check_growth"  = 1  look at the segment populations on the host before EVERY sort (default: only
+ *                        when the previous step's statistics say a segment may fill up; see
+ *                        picnix_cuda_get_growth_stats)
  *   "async_migration" = 1  multi-rank particle exchange without a host synchronisation: message
  *                        sizes follow from the previous step's counts (both sides compute the same
  *                        bound, get_comm_buffer returns send AND receive sizes, set_recv_bytes is not
@@ -213,6 +217,15 @@ int picnix_cuda_get_field_energy(picnix_arena_t* arena, double* efd, double* bfd
  * over interior cells of um[..][4]*c - um[..][0]*c^2 (rest mass subtracted); particle[nchunk*Ns].
  * Needs deposit_moment + the BoundaryMom exchange first, as in the reference. */
 int picnix_cuda_get_particle_energy(picnix_arena_t* arena, double* particle);
+/* Growing particle storage (XtensorParticle::resize, nix/xtensor_particle.hpp:70-115, as called by
+ * XtensorHaloParticle3D::pre_unpack, nix/xtensor_halo3d.hpp:406-418).  A (chunk, species) segment that
+ * fills up is enlarged before the particle exchange's sort; migrants that found it full wait on a spill
+ * list and are appended afterwards, so a run never aborts and never loses particles because a chunk's
+ * population grew.  segment_regrows: how often the particle arrays were re-laid out.  late_particles:
+ * migrants that were appended (or sent to a peer) one step late because the fill-up was not foreseen by
+ * the previous step's statistics; 0 in any Courant-limited run. */
+int picnix_cuda_get_growth_stats(const picnix_arena_t* arena, int64_t* segment_regrows,
+                                 int64_t* late_particles);
 /* counters since arena creation: kernels launched by this library, particles pushed */
 int picnix_cuda_get_counters(const picnix_arena_t* arena, int64_t* kernel_launches,
                              int64_t* particle_pushes);

@@ -94,6 +94,7 @@ SIGNATURES = {
     "picnix_cuda_get_diverror": (_i32, [_vp, _pd, _pd]),
     "picnix_cuda_get_field_energy": (_i32, [_vp, _pd, _pd]),
     "picnix_cuda_get_counters": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "picnix_cuda_get_growth_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "picnix_cuda_step_host": (_i32, [_vp, _dbl, _i32, _pd, _pd, _pd, _pd, _pi, _pi, _pi]),
     "picnix_cuda_upload_state": (_i32, [_vp, _pd, _pd, _pd, _pd, _pi, _pi]),
     "picnix_cuda_download_state": (_i32, [_vp, _pd, _pd, _pd, _pd, _pi, _pi]),

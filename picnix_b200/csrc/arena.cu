@@ -549,8 +549,8 @@ int picnix_cuda_synchronize(picnix_arena_t* a)
   if (flags[0] != 0)
     return fail(a, PICNIX_ERR_OVERFLOW,
                 "particle spill list overflow: more migrants than segments and spill list can hold in one step");
-  if (flags[1] != 0)
-    return fail(a, PICNIX_ERR_OVERFLOW, "particle migration send buffer overflow");
+  // flags[1] (a peer's message was full) is not an error any more: the records wait on the spill list and
+  // leave with the next exchange (grow.cu; counted by picnix_cuda_get_growth_stats)
   if (flags[2] != 0)
     return fail(a, PICNIX_ERR_INVALID,
                 "received a particle for a chunk/species this rank does not own (decomposition or "

@@ -40,6 +40,10 @@ int picnix_cuda_set_option(picnix_arena_t* a, const char* key, int64_t value)
     a->async_migration = value != 0;
     return PICNIX_OK;
   }
+  if (std::string(key) == "check_growth") {
+    a->check_growth_always = value != 0;
+    return PICNIX_OK;
+  }
   if (std::string(key) == "row_kernel") {
     if (value != 1 && value != 2)
       return fail(a, PICNIX_ERR_INVALID, "row_kernel must be 1 or 2");

@@ -15,7 +15,7 @@
 //   * particles leaving a chunk are appended straight behind the destination chunk's active
 //     particles (periodic wrap + cell key + histogram update included, i.e. post_unpack's work,
 //     nix/xtensor_halo3d.hpp:477-491), or into the peer's staging buffer as 64-byte records.
-#include "particle_common.cuh"
+#include "migrate.cuh"
 
 #include <algorithm>
 #include <tuple>
@@ -231,50 +231,6 @@ struct MigrateTables {
   const int64_t* psend_cap; // [npeer] capacity in records
   const int* nbid;       // [nchunk][27] global neighbour ids (for remote records)
 };
-
-// A migrant whose destination is full -- a segment, or the bounded message to a peer -- is kept in the
-// spill list instead of being dropped: tag.x >= 0 is the destination segment (re-appended by grow.cu once
-// the segment has grown), tag.x < 0 is ~(message slot) of a remote neighbour (re-sent with the next
-// exchange).  Only a full spill list loses particles, and that is an error.
-__device__ __forceinline__ void spill_particle(const DevPtrs& d, const double* p, int dest, int tagy)
-{
-  const int k = atomicAdd(d.spill_count, 1);
-  if (k >= d.spill_cap) {
-    atomicExch(d.errflag + 0, 1);
-    return;
-  }
-  double* out = d.spill_rec + (int64_t)k * 8;
-#pragma unroll
-  for (int c = 0; c < NC; c++)
-    out[c] = p[c];
-  int2 tag = make_int2(dest, tagy);
-  out[7]   = *reinterpret_cast<double*>(&tag);
-}
-
-// append one particle behind the active particles of (chunk, species); p = 7 components
-__device__ __forceinline__ void append_particle(const Geom& g, const DevPtrs& d, int chunk, int is,
-                                                double* p)
-{
-  const int seg  = chunk * g.Ns + is;
-  const int slot = atomicAdd(d.ntail + seg, 1);
-  const int ip   = d.np[seg] + slot;
-  if (ip >= d.seg_cap[seg]) {
-    // XtensorHaloParticle3D::pre_unpack would have resized first (nix/xtensor_halo3d.hpp:406-418): wait
-    // in the spill list for resolve_growth()
-    atomicSub(d.ntail + seg, 1);
-    spill_particle(d, p, seg, is);
-    return;
-  }
-  // post_unpack: periodic wrap, then count in the receiving chunk's geometry
-  wrap_periodic(g, p[0], p[1], p[2]);
-  const int64_t i = d.seg_off[seg] + ip;
-#pragma unroll
-  for (int k = 0; k < NC; k++)
-    d.xu[k * d.pcap + i] = p[k];
-  const int key = cell_key(g, d.clim + chunk * 6, p[0], p[1], p[2]);
-  d.gindex[i]   = key;
-  atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, 1);
-}
 
 // send one particle that left (chunk, species) to the neighbour its position points at
 __device__ __forceinline__ void migrate_particle(const Geom& g, const DevPtrs& d,
@@ -630,6 +586,79 @@ static bool migration_history_ready(const picnix_arena* a)
   return !a->peers.empty();
 }
 
+// spilled records with a remote destination (tag.x = ~message slot) -> the peer's send buffer, first in
+// line; whatever does not fit (or waits for a local segment) stays on the list
+__global__ void __launch_bounds__(HALO_THREADS)
+resend_spill_kernel(DevPtrs d, MigrateTables tab, int n, double* __restrict__ keep, int* __restrict__ nkeep)
+{
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const double* in      = d.spill_rec + (int64_t)r * 8;
+    double        tagbits = in[7];
+    const int2    tag     = *reinterpret_cast<int2*>(&tagbits);
+    bool          sent    = false;
+    if (tag.x < 0) {
+      const int peer = tab.slot_peer[~tag.x];
+      const int rec  = atomicAdd(tab.psend_cnt[peer], 1);
+      if (rec < tab.psend_cap[peer]) {
+        double* out = tab.psend[peer] + (int64_t)rec * 8;
+#pragma unroll
+        for (int k = 0; k < NC; k++)
+          out[k] = in[k];
+        int2 dst = make_int2(tag.y & 0xffffff, tag.y >> 24); // global chunk id, species
+        out[7]   = *reinterpret_cast<double*>(&dst);
+        sent     = true;
+      } else {
+        atomicSub(tab.psend_cnt[peer], 1);
+      }
+    }
+    if (!sent) {
+      const int k   = atomicAdd(nkeep, 1);
+      double*   out = keep + (int64_t)k * 8;
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+        out[c] = in[c];
+    }
+  }
+}
+
+static int resend_spilled(picnix_arena* a, const MigrateTables& tab)
+{
+  // the statistics of the previous step say whether anything is waiting (one step late is enough: a
+  // record spilled in step n is looked at in step n + 1 by resolve_growth and leaves in step n + 2 at
+  // the latest)
+  if (a->stat_pending) {
+    PICNIX_CUDA(a, cudaEventSynchronize(a->stat_event));
+    a->stat_minfree = a->h_stat[0];
+    a->stat_maxtail = a->h_stat[1];
+    a->stat_spilled = a->h_stat[2];
+    a->stat_pending = false;
+    a->stat_known   = true;
+  }
+  if (!a->stat_known || a->stat_spilled <= 0)
+    return PICNIX_OK;
+  int n = 0;
+  PICNIX_CUDA(a, cudaMemcpyAsync(&n, a->d.spill_count, sizeof(int), cudaMemcpyDeviceToHost, a->stream));
+  PICNIX_CUDA(a, cudaStreamSynchronize(a->stream));
+  n = std::min(n, a->d.spill_cap);
+  if (n <= 0)
+    return PICNIX_OK;
+  double* keep  = nullptr;
+  int*    nkeep = nullptr;
+  PICNIX_CUDA(a, cudaMalloc((void**)&keep, (size_t)n * 8 * sizeof(double)));
+  PICNIX_CUDA(a, cudaMalloc((void**)&nkeep, sizeof(int)));
+  PICNIX_CUDA(a, cudaMemsetAsync(nkeep, 0, sizeof(int), a->stream));
+  resend_spill_kernel<<<std::min(148 * 2, (n + HALO_THREADS - 1) / HALO_THREADS), HALO_THREADS, 0, a->stream>>>(
+      a->d, tab, n, keep, nkeep);
+  a->kernel_launches++;
+  PICNIX_CUDA(a, cudaMemcpyAsync(a->d.spill_rec, keep, (size_t)n * 8 * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 a->stream));
+  PICNIX_CUDA(a, cudaMemcpyAsync(a->d.spill_count, nkeep, sizeof(int), cudaMemcpyDeviceToDevice, a->stream));
+  PICNIX_CUDA(a, cudaStreamSynchronize(a->stream));
+  cudaFree(keep);
+  cudaFree(nkeep);
+  return PICNIX_OK;
+}
+
 int launch_halo_begin(picnix_arena* a, int mode)
 {
   const Geom& g      = a->g;
@@ -724,6 +753,12 @@ int launch_halo_begin(picnix_arena* a, int mode)
     if (!a->peers.empty())
       PICNIX_CUDA(a, cudaMemcpyAsync(a->d_psend_caps, a->h_bounds, a->peers.size() * sizeof(int64_t),
                                      cudaMemcpyHostToDevice, a->stream));
+    if (!a->peers.empty()) {
+      // records that did not fit a peer's message in an earlier step leave first
+      MigrateTables tab{a->d_slot_peer, a->d_psend_ptrs, a->d_psend_cnts, a->d_psend_caps, a->d_slot_dst};
+      if ((status = resend_spilled(a, tab)) != PICNIX_OK)
+        return status;
+    }
     int maxcap = 0;
     for (int s = 0; s < a->nseg; s++)
       maxcap = std::max(maxcap, a->seg_cap[s]);
@@ -836,8 +871,13 @@ int launch_halo_end(picnix_arena* a, int mode)
         p.last_recv = nrec;
       }
     }
+    // pre_unpack would have resized the particle arrays (nix/xtensor_halo3d.hpp:406-418): grow the segments
+    // that are (nearly) full and append the migrants that were waiting for room
+    int status = resolve_growth(a);
+    if (status != PICNIX_OK)
+      return status;
     // post_unpack ends with sort() for every species (nix/xtensor_halo3d.hpp:495-497)
-    int status = launch_sort(a, 0, -1);
+    status = launch_sort(a, 0, -1);
     if (status != PICNIX_OK)
       return status;
     break;

@@ -169,9 +169,9 @@ __global__ void finish_kernel(Geom g, DevPtrs d, int seg0, int nseg)
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nseg)
     return;
-  int seg      = seg0 + t;
-  d.np[seg]    = d.pindex[(int64_t)seg * (g.Ng + 1) + g.Ng];
-  d.ntail[seg] = 0;
+  int seg   = seg0 + t;
+  d.np[seg] = d.pindex[(int64_t)seg * (g.Ng + 1) + g.Ng];
+  // ntail (the arrivals of this step) is read by the growth statistics and cleared there
 }
 
 } // namespace
@@ -217,6 +217,12 @@ int launch_sort(picnix_arena* a, int c0, int cn)
   finish_kernel<<<(nseg + 127) / 128, 128, 0, a->stream>>>(g, a->d, seg0, nseg);
   a->kernel_launches++;
   PICNIX_CUDA(a, cudaGetLastError());
+  {
+    // smallest free space / largest number of arrivals / spill count: the next step's growth decision
+    int status = record_segment_stats(a);
+    if (status != PICNIX_OK)
+      return status;
+  }
 
   if (lazy) {
     a->perm_pending = true;

@@ -96,6 +96,12 @@ class CudaSim:
         self._check(self.lib.picnix_cuda_get_counters(self.h, C.byref(launches), C.byref(pushes)))
         return launches.value, pushes.value
 
+    def growth_stats(self):
+        """(segment re-layouts, migrants delivered one step late) since the arena was created."""
+        regrows, late = C.c_int64(), C.c_int64()
+        self._check(self.lib.picnix_cuda_get_growth_stats(self.h, C.byref(regrows), C.byref(late)))
+        return regrows.value, late.value
+
     # -- decomposition ---------------------------------------------------------------------
     def chunkmap(self):
         return capi.sfc_build(*tuple(self.cfg.cdims))

@@ -1,0 +1,63 @@
+"""GPU: particle storage grows on demand (XtensorParticle::resize, nix/xtensor_particle.hpp:70-115, as
+XtensorHaloParticle3D::pre_unpack calls it, nix/xtensor_halo3d.hpp:406-418) instead of aborting.
+
+A plasma that converges on the centre of one chunk loads that chunk to several times its initial
+population (its segments were allocated with the usual 20 % slack).  The run must continue, lose no
+particle and stay on the reference's trajectory: Np / pindex bit-exact, fields within the multi-step
+tolerance.  The reference resizes its arrays every step; here the segments are re-laid out when the
+previous step's statistics say one may fill up (picnix_cuda_get_growth_stats counts how often).
+"""
+import numpy as np
+import pytest
+
+from helpers import FIELD_UF, FIELD_UJ, cells_consistent, counts_equal, field_err, particle_err
+from oracle import ref_backend
+from picnix_b200 import problems
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_backend.available(), reason="oracle/_ref not built")]
+
+NDIMS, CDIMS, PPC = (16, 16, 16), (2, 2, 2), (8, 8)
+SPECIES = [dict(qm=-1.0, ro=1e-3), dict(qm=+0.1, ro=1e-2)]   # tenuous: the flow stays ballistic
+
+
+def converging_setup(sim, rate, centre=(4.0, 4.0, 4.0), seed=11):
+    dims = problems.chunk_dims(NDIMS, CDIMS)
+    _, coord = sim.chunkmap()
+    for isp, (q, m) in enumerate(problems.species_charge_mass(SPECIES, PPC)):
+        sim.set_species(isp, q, m)
+    for ic in range(sim.nchunk):
+        sim.set_field(ic, FIELD_UF, np.zeros(sim.shape + (6,)))
+        parts = problems.make_chunk_particles(ic, coord[ic], dims, 1.0, [dict(vt=0.0), dict(vt=0.0)], PPC, seed)
+        for isp, xu in enumerate(parts):
+            xu[:, 3:6] = -rate * (1.0 - 0.2 * isp) * (xu[:, 0:3] - np.asarray(centre))  # species separate: J != 0
+            sim.set_particles(ic, isp, xu)
+    sim.finalize_setup()
+
+
+@pytest.mark.parametrize("always_check", [0, 1])
+def test_chunk_loaded_to_several_times_its_initial_count(always_check):
+    from picnix_b200 import CudaSim
+
+    kw = dict(Ns=2, cc=1.0, delh=1.0, order=2, pusher=0, interp=0)
+    ref = ref_backend.RefSim(NDIMS, CDIMS, vector_mode=1, **kw)
+    gpu = CudaSim(NDIMS, CDIMS, **kw)
+    gpu.set_option("check_growth", always_check)
+    dt, rate, nstep = 0.4, 0.1, 40         # c dt / dx = 0.4; momenta up to 1.1 c, at most 0.3 cells per step
+    for sim in (ref, gpu):
+        converging_setup(sim, rate)
+    n0 = gpu.get_np_all().copy()
+    total0 = int(n0.sum())
+    ref.step(dt, nstep)
+    gpu.step(dt, nstep)
+    gpu.synchronize()          # no overflow error
+    n1 = gpu.get_np_all()
+    assert int(n1.sum()) == total0                      # nothing lost
+    assert n1.max() > 3 * n0.max()                      # one chunk holds several times its initial count
+    regrows, late = gpu.growth_stats()
+    assert regrows >= 1 and late == 0
+    assert counts_equal(gpu, ref)
+    assert cells_consistent(gpu, NDIMS, CDIMS)
+    assert field_err(gpu, ref, FIELD_UF) < 1e-9
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-9
+    dx, du, same = particle_err(gpu, ref, scale_x=16.0, scale_u=1.0)
+    assert same and dx < 1e-10 and du < 1e-10
