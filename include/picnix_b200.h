@@ -55,6 +55,12 @@ extern "C" {
 #define PICNIX_FIELD_FF 2 /* [Mz][My][Mx][3][6]     */
 #define PICNIX_FIELD_UM 3 /* [Mz][My][Mx][Ns][14]   */
 
+/* physical boundary conditions on the faces of a non-periodic direction (picnix_cuda_set_boundary_condition) */
+#define PICNIX_BC_NONE 0       /* open: fields as the halo exchange left them, particles leave          */
+#define PICNIX_BC_CONDUCTING 1 /* conducting wall, specular reflection (example/mrx/main.cpp:183-382)   */
+#define PICNIX_BC_WALL 2       /* shock-tube wall, momentum reversed (example/shock/main.cpp:232-283)   */
+#define PICNIX_BC_INFLOW 3     /* upstream values imposed (example/shock/main.cpp:285-340)              */
+
 /* pusher / interpolation enums, pic/engine/velocity.hpp:12-28 */
 #define PICNIX_PUSHER_BORIS 0
 #define PICNIX_PUSHER_VAY 1
@@ -122,6 +128,25 @@ const char* picnix_cuda_last_error(const picnix_arena_t* arena);
  *                        bound, get_comm_buffer returns send AND receive sizes, set_recv_bytes is not
  *                        needed), the actual count travels in a 64-byte header behind the records */
 int picnix_cuda_set_option(picnix_arena_t* arena, const char* key, int64_t value);
+
+/*
+ * Physical boundary condition of one face of the global domain: axis 0 = z, 1 = y, 2 = x; side 0 = lower,
+ * 1 = upper.  Replaces the set_boundary_field / set_boundary_particle hooks a problem's MainChunk
+ * overrides in the reference (pic/pic_chunk.hpp:122-126): the fields are treated after every field halo
+ * exchange, the particles right after the position push (before the cell count and the deposit).
+ * PICNIX_BC_CONDUCTING is available for walls normal to y, PICNIX_BC_WALL for the lower and
+ * PICNIX_BC_INFLOW for the upper x boundary (values = Ex, Ey, Ez, Bx, By, Bz imposed in the margin) --
+ * the kinds and faces the reference's examples use.  The direction must be non-periodic in the arena's
+ * configuration.
+ */
+int picnix_cuda_set_boundary_condition(picnix_arena_t* arena, int32_t axis, int32_t side, int32_t kind,
+                                       const double* values /* [6] or NULL */);
+
+/* PicChunk::inject_particle hook (pic/pic_chunk.hpp:128): append `n` host-generated particles (AoS [n][7])
+ * to (chunk, species); call between boundary_begin and boundary_end of PICNIX_BOUNDARY_PARTICLE, whose
+ * sort takes them in.  Segments grow as needed (picnix_cuda_get_growth_stats). */
+int picnix_cuda_inject_particles(picnix_arena_t* arena, int32_t ichunk, int32_t is, const double* xu_aos,
+                                 int32_t n);
 
 /* use an existing CUDA stream (cudaStream_t as void*); default is a stream the arena owns */
 int picnix_cuda_set_stream(picnix_arena_t* arena, void* stream);

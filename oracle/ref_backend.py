@@ -28,6 +28,7 @@ class RefConfig(C.Structure):
         ("Ns", C.c_int32),
         ("vector_mode", C.c_int32),
         ("nthread", C.c_int32),
+        ("problem", C.c_int32),
         ("cc", C.c_double),
         ("delh", C.c_double),
         ("friedman", C.c_double),
@@ -87,6 +88,8 @@ def load():
         "ref_get_neighbors": (None, [vp, i32, pi, pi]),
         "ref_chunkmap_validate": (i32, [vp]),
         "ref_set_species": (None, [vp, i32, dbl, dbl]),
+        "ref_get_species": (None, [vp, i32, C.POINTER(dbl), C.POINTER(dbl)]),
+        "ref_set_problem_json": (None, [C.c_char_p]),
         "ref_set_field": (None, [vp, i32, i32, pd]),
         "ref_get_field": (None, [vp, i32, i32, pd]),
         "ref_set_particles": (None, [vp, i32, i32, pd, i32, i32]),
@@ -122,10 +125,22 @@ class RefSim:
 
     name = "reference"
 
+    PROBLEMS = {None: 0, "plain": 0, "mrx": 1, "shock": 2}
+
     def __init__(self, ndims, cdims, Ns, cc, delh=1.0, order=2, pusher=0, interp=0, periodic=(1, 1, 1),
-                 friedman=0.0, buffer_ratio=0.2, vector_mode=1, nthread=0):
+                 friedman=0.0, buffer_ratio=0.2, vector_mode=1, nthread=0, problem=None, problem_json=None):
+        """problem: None / "mrx" / "shock" -- the chunks are the example's MainChunk, i.e. its physical
+        boundary hooks (set_boundary_field / set_boundary_particle / inject_particle) are active.
+        problem_json: dict merged into the chunk configuration; with "example_setup": True the example's
+        own MainChunk::setup builds the initial state (Harris sheet, shock tube), otherwise the state
+        comes through set_field / set_particles as usual."""
         self.lib = load()
+        if problem_json is not None:
+            import json
+
+            self.lib.ref_set_problem_json(json.dumps(problem_json).encode())
         cfg = RefConfig()
+        cfg.problem = self.PROBLEMS[problem]
         cfg.ndims[:] = ndims
         cfg.cdims[:] = cdims
         cfg.periodic[:] = periodic

@@ -13,11 +13,29 @@
 // MPI message flow, particle migration and sort are all the reference's own code.
 #include "nix/balancer.hpp"
 #include "nix/chunkmap.hpp"
+#include "nix/random.hpp"
+#include "pic_application.hpp"
 #include "pic_chunk.hpp"
+#include "pic_diag.hpp"
+
+// The problem code of the reference's examples with physical boundaries, read in place and UNCHANGED:
+// MainChunk::{setup, set_boundary_field, set_boundary_particle, inject_particle} of
+// example/mrx/main.cpp (conducting walls in y, Harris sheet) and example/shock/main.cpp (wall at the
+// lower x boundary, injection at the upper one).  Their headers are included above, so inside the
+// namespaces only the example's own classes (and its main()) are declared.
+namespace mrx_ex
+{
+#include "example/mrx/main.cpp"
+}
+namespace shock_ex
+{
+#include "example/shock/main.cpp"
+}
 
 #include <omp.h>
 
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <vector>
 
@@ -36,55 +54,128 @@ struct RefConfig {
   int32_t Ns;          // number of species
   int32_t vector_mode; // 0: reference 'scalar' kernels, 1: reference 'vector' kernels
   int32_t nthread;     // OpenMP threads for the chunk loops (<=0: all)
+  int32_t problem;     // 0: plain PicChunk, 1: example/mrx MainChunk, 2: example/shock MainChunk
   double  cc;
   double  delh;
   double  friedman;
   double  buffer_ratio;
 };
 
-class RefChunk : public PicChunk
+// What the driver needs from a chunk, whatever class it is built on: the PicChunk entry points and the
+// (protected) arrays, reached through accessors the concrete class below provides.
+struct RefArrays {
+  xt::xtensor<float64, 4>* uf;
+  xt::xtensor<float64, 4>* uj;
+  xt::xtensor<float64, 5>* um;
+  xt::xtensor<float64, 5>* ff;
+  ParticleVec*             up;
+  int*                     Ns;
+  json*                    option;
+};
+
+class RefChunk
 {
 public:
-  using PicChunk::PicChunk;
+  std::unique_ptr<PicChunk> chunk;
+  std::function<RefArrays()> arrays;
+
+  PicChunk& pic() { return *chunk; }
+  auto&     ref_uf() { return *arrays().uf; }
+  auto&     ref_uj() { return *arrays().uj; }
+  auto&     ref_um() { return *arrays().um; }
+  auto&     ref_ff() { return *arrays().ff; }
+  auto&     ref_up() { return *arrays().up; }
+  int       ref_Ns() { return *arrays().Ns; }
+  json&     ref_option() { return *arrays().option; }
+
+  // forwarding of the PicChunk entry points the driver calls
+  void push_bfd(double dt) { pic().push_bfd(dt); }
+  void push_efd(double dt) { pic().push_efd(dt); }
+  void push_velocity(double dt) { pic().push_velocity(dt); }
+  void push_position(double dt) { pic().push_position(dt); }
+  void deposit_current(double dt) { pic().deposit_current(dt); }
+  void deposit_moment() { pic().deposit_moment(); }
+  void sort_particle(ParticleVec& p) { pic().sort_particle(p); }
+  void init_friedman() { pic().init_friedman(); }
+  void reset_load() { pic().reset_load(); }
+  void set_boundary_pack(int mode) { pic().set_boundary_pack(mode); }
+  void set_boundary_begin(int mode) { pic().set_boundary_begin(mode); }
+  bool set_boundary_probe(int mode, bool wait) { return pic().set_boundary_probe(mode, wait); }
+  void set_boundary_end(int mode) { pic().set_boundary_end(mode); }
+  void set_boundary_unpack(int mode) { pic().set_boundary_unpack(mode); }
+  void get_diverror(double& e, double& b) { pic().get_diverror(e, b); }
+  void get_energy(double& e, double& b, double* p) { pic().get_energy(e, b, p); }
+  int  get_nb_id(int dz, int dy, int dx) { return pic().get_nb_id(dz, dy, dx); }
+  int  get_nb_rank(int dz, int dy, int dx) { return pic().get_nb_rank(dz, dy, dx); }
+  int  get_boundary_margin() { return pic().get_boundary_margin(); }
+};
+
+// Base = PicChunk (periodic problems: the state comes through the C API) or an example's MainChunk
+// (its boundary hooks apply; its own setup() runs when the configuration carries the example's
+// parameters, otherwise the plain set-up below, so that any state can be fed to the example's hooks).
+template <typename Base, bool IsExample>
+class RefChunkT : public Base
+{
+public:
+  using Base::Base;
+
+  RefArrays arrays() { return {&this->uf, &this->uj, &this->um, &this->ff, &this->up, &this->Ns, &this->option}; }
 
   virtual void setup(json& config) override
   {
+    if (IsExample && config.value("example_setup", false)) {
+      Base::setup(config); // MainChunk::setup of the example: fields, particles, sort
+      return;
+    }
     PicChunk::setup(config); // pic/pic_chunk.cpp:135-262
 
-    Ns           = config["Ns"].get<int>();
-    cc           = config["cc"].get<float64>();
-    float64 delh = config["delh"].get<float64>();
-    set_coordinate(delh, delh, delh);
-    allocate();
+    this->Ns     = config["Ns"].template get<int>();
+    this->cc     = config["cc"].template get<float64>();
+    float64 delh = config["delh"].template get<float64>();
+    this->set_coordinate(delh, delh, delh);
+    this->allocate();
 
     // same buffer setup as every example's MainChunk::setup (example/thermal/main.cpp:56-59)
-    this->set_mpi_buffer(mpibufvec[BoundaryEmf], 0, 0, sizeof(float64) * 6);
-    this->set_mpi_buffer(mpibufvec[BoundaryCur], 0, 0, sizeof(float64) * 4);
-    this->set_mpi_buffer(mpibufvec[BoundaryMom], 0, 0, sizeof(float64) * Ns * 14);
+    this->set_mpi_buffer(this->mpibufvec[BoundaryEmf], 0, 0, sizeof(float64) * 6);
+    this->set_mpi_buffer(this->mpibufvec[BoundaryCur], 0, 0, sizeof(float64) * 4);
+    this->set_mpi_buffer(this->mpibufvec[BoundaryMom], 0, 0, sizeof(float64) * this->Ns * 14);
 
-    up.resize(Ns);
-    for (int is = 0; is < Ns; is++) {
-      up[is]     = std::make_shared<ParticleType>(0, *this);
-      up[is]->Np = 0;
-      up[is]->q  = 0;
-      up[is]->m  = 1;
+    this->up.resize(this->Ns);
+    for (int is = 0; is < this->Ns; is++) {
+      this->up[is]     = std::make_shared<ParticleType>(0, *this);
+      this->up[is]->Np = 0;
+      this->up[is]->q  = 0;
+      this->up[is]->m  = 1;
     }
+    if (IsExample && config.contains("boundary"))
+      this->option["boundary"] = config["boundary"]; // example/shock reads its wall / inflow values here
   }
 
-  // non-periodic faces: the base class only logs an error (pic/pic_chunk.cpp:455-481); the
-  // physical boundary condition itself is problem code, which is out of scope here
+  // plain chunks on non-periodic faces: the base class only logs an error (pic/pic_chunk.cpp:455-481)
   virtual void set_boundary_field(int mode) override
   {
+    if (IsExample)
+      Base::set_boundary_field(mode);
   }
 
-  auto& ref_uf() { return uf; }
-  auto& ref_uj() { return uj; }
-  auto& ref_um() { return um; }
-  auto& ref_ff() { return ff; }
-  auto& ref_up() { return up; }
-  int   ref_Ns() const { return Ns; }
-  json& ref_option() { return option; }
 };
+
+template <typename T>
+std::unique_ptr<RefChunk> make_chunk(const int dims[3], const bool has_dim[3], int id)
+{
+  auto typed   = std::make_unique<T>(dims, has_dim, id);
+  T*   raw     = typed.get();
+  auto wrapper = std::make_unique<RefChunk>();
+  wrapper->chunk  = std::move(typed);
+  wrapper->arrays = [raw]() { return raw->arrays(); };
+  return wrapper;
+}
+
+using PlainChunk = RefChunkT<PicChunk, false>;
+using MrxChunk   = RefChunkT<mrx_ex::MainChunk, true>;
+using ShockChunk = RefChunkT<shock_ex::MainChunk, true>;
+
+std::string g_problem_json; // parameters of the example's own setup(), set by ref_set_problem_json
 
 struct RefSim {
   RefConfig                              cfg;
@@ -122,6 +213,14 @@ void exchange(RefSim* sim, int mode)
 } // namespace
 
 extern "C" {
+
+// JSON text with the example's own parameters; consumed by the next ref_create (problem 1 or 2), whose
+// chunks then run the example's MainChunk::setup (key "example_setup": true) or only take its boundary
+// values (key "boundary")
+void ref_set_problem_json(const char* text)
+{
+  g_problem_json = text ? text : "";
+}
 
 void* ref_create(const RefConfig* cfg)
 {
@@ -173,8 +272,28 @@ void* ref_create(const RefConfig* cfg)
                       {"friedman", cfg->friedman},
                       {"buffer_ratio", cfg->buffer_ratio}};
 
+  if (!g_problem_json.empty()) {
+    // the example's own parameters (config.toml [parameter]) on top of the driver's; its setup() runs
+    json extra = json::parse(g_problem_json);
+    for (auto it = extra.begin(); it != extra.end(); ++it) {
+      if (it.key() == "option") {
+        for (auto jt = it.value().begin(); jt != it.value().end(); ++jt)
+          config["option"][jt.key()] = jt.value();
+      } else {
+        config[it.key()] = it.value();
+      }
+    }
+    g_problem_json.clear();
+  }
+
   for (int id = 0; id < nc; id++) {
-    auto chunk = std::make_unique<RefChunk>(dims, has_dim, id);
+    std::unique_ptr<RefChunk> chunk;
+    if (cfg->problem == 1)
+      chunk = make_chunk<MrxChunk>(dims, has_dim, id);
+    else if (cfg->problem == 2)
+      chunk = make_chunk<ShockChunk>(dims, has_dim, id);
+    else
+      chunk = make_chunk<PlainChunk>(dims, has_dim, id);
 
     // nix/chunkvector.hpp:56-81
     auto [cz, cy, cx] = sim->chunkmap->get_coordinate(id);
@@ -185,22 +304,22 @@ void* ref_create(const RefConfig* cfg)
           int ny   = sim->chunkmap->get_neighbor_coord(cy, diry, 1);
           int nx   = sim->chunkmap->get_neighbor_coord(cx, dirx, 2);
           int nbid = sim->chunkmap->get_chunkid(nz, ny, nx);
-          chunk->set_nb_id(dirz, diry, dirx, nbid);
-          chunk->set_nb_rank(dirz, diry, dirx, sim->chunkmap->get_rank(nbid));
+          chunk->pic().set_nb_id(dirz, diry, dirx, nbid);
+          chunk->pic().set_nb_rank(dirz, diry, dirx, sim->chunkmap->get_rank(nbid));
         }
       }
     }
 
     // nix/application.cpp:291-300
     int offset[3] = {cz * nd[0] / cd[0], cy * nd[1] / cd[1], cx * nd[2] / cd[2]};
-    chunk->set_global_context(offset, nd);
-    chunk->setup(config);
+    chunk->pic().set_global_context(offset, nd);
+    chunk->pic().setup(config);
 
     for (int mode = 0; mode < NumBoundaryMode; mode++)
       for (int iz = 0; iz < 3; iz++)
         for (int iy = 0; iy < 3; iy++)
           for (int ix = 0; ix < 3; ix++)
-            chunk->set_mpi_communicator(mode, iz, iy, ix, sim->comm[mode][iz][iy][ix]);
+            chunk->pic().set_mpi_communicator(mode, iz, iy, ix, sim->comm[mode][iz][iy][ix]);
 
     sim->chunks.push_back(std::move(chunk));
   }
@@ -271,6 +390,13 @@ int ref_chunkmap_validate(void* handle)
   return static_cast<RefSim*>(handle)->chunkmap->validate() ? 1 : 0;
 }
 
+void ref_get_species(void* handle, int is, double* q, double* m)
+{
+  auto sim = static_cast<RefSim*>(handle);
+  *q       = sim->chunks[0]->ref_up()[is]->q;
+  *m       = sim->chunks[0]->ref_up()[is]->m;
+}
+
 void ref_set_species(void* handle, int is, double q, double m)
 {
   auto sim = static_cast<RefSim*>(handle);
@@ -324,7 +450,7 @@ void ref_set_particles(void* handle, int ichunk, int is, const double* xu, int n
   auto  chunk = sim->chunks[ichunk].get();
   auto& up    = chunk->ref_up();
   double q = up[is]->q, m = up[is]->m;
-  up[is]     = std::make_shared<ParticleType>(np_alloc, *chunk);
+  up[is]     = std::make_shared<ParticleType>(np_alloc, chunk->pic());
   up[is]->q  = q;
   up[is]->m  = m;
   up[is]->Np = np;

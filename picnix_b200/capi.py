@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpicnix_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_OVERFLOW, ERR_NODEVICE = 0, 1, 2, 3, 4
+BC_NONE, BC_CONDUCTING, BC_WALL, BC_INFLOW = 0, 1, 2, 3
 BOUNDARY_EMF, BOUNDARY_CUR, BOUNDARY_MOM, BOUNDARY_PARTICLE = 0, 1, 2, 3
 FIELD_UF, FIELD_UJ, FIELD_FF, FIELD_UM = 0, 1, 2, 3
 PUSHER_BORIS, PUSHER_VAY, PUSHER_HIGUERA_CARY = 0, 1, 2
@@ -95,6 +96,8 @@ SIGNATURES = {
     "picnix_cuda_get_field_energy": (_i32, [_vp, _pd, _pd]),
     "picnix_cuda_get_counters": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "picnix_cuda_get_growth_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "picnix_cuda_set_boundary_condition": (_i32, [_vp, _i32, _i32, _i32, C.c_void_p]),
+    "picnix_cuda_inject_particles": (_i32, [_vp, _i32, _i32, _pd, _i32]),
     "picnix_cuda_step_host": (_i32, [_vp, _dbl, _i32, _pd, _pd, _pd, _pd, _pi, _pi, _pi]),
     "picnix_cuda_upload_state": (_i32, [_vp, _pd, _pd, _pd, _pd, _pi, _pi]),
     "picnix_cuda_download_state": (_i32, [_vp, _pd, _pd, _pd, _pd, _pi, _pi]),

@@ -48,6 +48,10 @@ struct Geom {
   double del[3];     // dz, dy, dx
   double glim[3][2]; // global domain [z|y|x][min|max], nix/chunk.cpp:210-237
   double theta;      // Friedman filter parameter
+  // physical boundary conditions on non-periodic faces (boundary.cu): kind and values per [z|y|x][lower|upper]
+  int    bc_kind[3][2];
+  int    any_particle_bc; // some face reflects particles
+  double bc_val[3][2][6]; // PICNIX_BC_INFLOW: Ex, Ey, Ez, Bx, By, Bz imposed in the margin
 };
 
 // Per-arena device pointers; passed BY VALUE to kernels.
@@ -165,6 +169,7 @@ struct picnix_arena {
   cudaEvent_t            mig_event  = nullptr;
   bool                   mig_pending = false;     // h_mig will hold the counts of the last step after mig_event
   bool                   perm_pending = false;  // xu is NOT yet in pindex order: DevPtrs::perm holds the order
+  bool                   any_bc        = false; // some face has a physical boundary condition (boundary.cu)
   bool                   force_generic = false; // testing: bypass the tiled kernels
   bool                   deposit_mma   = false; // row kernel variant: deposit through the FP64 MMA unit
   int                    row_version   = 2;     // option "row_kernel": 2 = rowpush.cu, 1 = round-1 kernel (rowfused.cu)
@@ -236,6 +241,7 @@ int materialize_sort(picnix_arena* a); // physically order xu if an index-only s
 
 int resolve_growth(picnix_arena* a);  // grow.cu: before the sort of the particle exchange
 int record_segment_stats(picnix_arena* a);
+int launch_boundary_field(picnix_arena* a, int mode); // boundary.cu: PicChunk::set_boundary_field
 int launch_halo_begin(picnix_arena* a, int mode);
 int launch_halo_end(picnix_arena* a, int mode);
 

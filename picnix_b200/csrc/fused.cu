@@ -60,6 +60,7 @@ fused_generic_kernel(Geom g, DevPtrs d, int c0, int blocks_per_seg, double delt)
 
   double x1 = x0, y1 = y0, z1 = z0;
   push_position(x1, y1, z1, ux, uy, uz, 1 / g.cc, delt);
+  apply_particle_bc(g, x1, y1, z1, ux, uy, uz);
 
   d.xu[0 * d.pcap + i] = x1;
   d.xu[1 * d.pcap + i] = y1;

@@ -885,7 +885,44 @@ int launch_halo_end(picnix_arena* a, int mode)
   default:
     return fail(a, PICNIX_ERR_INVALID, "No such boundary mode exists!");
   }
+  {
+    // PicChunk::set_boundary_unpack ends with the physical boundary hook (pic/pic_chunk.cpp:360-361)
+    int status = launch_boundary_field(a, mode);
+    if (status != PICNIX_OK)
+      return status;
+  }
   return check_cuda(a, cudaGetLastError(), "boundary_end");
+}
+
+// PicChunk::inject_particle hook (called by set_boundary_pack(BoundaryParticle), pic/pic_chunk.cpp:305-310):
+// particles the host generated (example/shock/main.cpp:436-535 draws them from the host's generators) are
+// appended behind the active particles of (chunk, species), keyed and counted, before the exchange's sort
+__global__ void __launch_bounds__(HALO_THREADS)
+inject_kernel(Geom g, DevPtrs d, const double* __restrict__ aos, int n, int chunk, int is)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n)
+    return;
+  double p[NC];
+#pragma unroll
+  for (int k = 0; k < NC; k++)
+    p[k] = aos[(int64_t)r * NC + k];
+  append_particle(g, d, chunk, is, p);
+}
+
+int inject_particles(picnix_arena* a, int ichunk, int is, const double* aos, int n)
+{
+  if (n <= 0)
+    return PICNIX_OK;
+  double* dbuf = nullptr;
+  PICNIX_CUDA(a, cudaMalloc((void**)&dbuf, (size_t)n * NC * sizeof(double)));
+  PICNIX_CUDA(a, cudaMemcpyAsync(dbuf, aos, (size_t)n * NC * sizeof(double), cudaMemcpyHostToDevice, a->stream));
+  inject_kernel<<<(n + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, 0, a->stream>>>(a->g, a->d, dbuf, n, ichunk, is);
+  a->kernel_launches++;
+  PICNIX_CUDA(a, cudaStreamSynchronize(a->stream));
+  cudaFree(dbuf);
+  a->leave_list_valid = false;
+  return check_cuda(a, cudaGetLastError(), "inject_particles");
 }
 
 } // namespace picnix
@@ -893,6 +930,17 @@ int launch_halo_end(picnix_arena* a, int mode)
 using namespace picnix;
 
 extern "C" {
+
+int picnix_cuda_inject_particles(picnix_arena_t* a, int32_t ichunk, int32_t is, const double* xu_aos, int32_t n)
+{
+  if (a == nullptr || ichunk < 0 || ichunk >= a->g.nchunk || is < 0 || is >= a->g.Ns || n < 0 ||
+      (xu_aos == nullptr && n > 0) || !a->particles_allocated)
+    return PICNIX_ERR_INVALID;
+  int status = materialize_sort(a);
+  if (status != PICNIX_OK)
+    return status;
+  return inject_particles(a, ichunk, is, xu_aos, n);
+}
 
 int picnix_cuda_get_peers(const picnix_arena_t* a, int32_t* npeer, int32_t* peer_rank)
 {

@@ -96,6 +96,12 @@ position_kernel(Geom g, DevPtrs d, int c0, int blocks_per_seg, double delt)
   }
 
   push_position(p[0], p[1], p[2], p[3], p[4], p[5], 1 / g.cc, delt);
+  if (g.any_particle_bc) {
+    apply_particle_bc(g, p[0], p[1], p[2], p[3], p[4], p[5]);
+    d.xu[3 * d.pcap + i] = p[3];
+    d.xu[4 * d.pcap + i] = p[4];
+    d.xu[5 * d.pcap + i] = p[5];
+  }
 
   d.xu[0 * d.pcap + i] = p[0];
   d.xu[1 * d.pcap + i] = p[1];

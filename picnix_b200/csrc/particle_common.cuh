@@ -2,6 +2,10 @@
 // Device building blocks of the particle kernels: cell lookup, shape functions, momentum pushers
 // and the per-dimension weight set-up shared by the velocity push and the current deposit.
 //
+// The pushers and the WT shape functions below are closed-form formulas whose operation order is pinned
+// by the parity bar (1e-13 against the reference on identical inputs): they follow nix/primitives.hpp
+// term by term, including its temporaries, because any re-association shows up in the last digits.
+//
 // Reference (all scalar forms; the xsimd forms compute the same numbers lane-wise):
 //   digitize                     nix/primitives.hpp:45-58
 //   lorentz_factor               nix/primitives.hpp:157-161
@@ -293,6 +297,40 @@ __device__ __forceinline__ void push_position(double& x, double& y, double& z, d
   x += ux * dt;
   y += uy * dt;
   z += uz * dt;
+}
+
+// Physical boundary of the problem for a particle that has just been moved: the set_boundary_particle
+// hooks of the reference's examples, called between the position push and the cell count
+// (pic/pic_engine.hpp:292-303).  A conducting wall reflects specularly (example/mrx/main.cpp:352-382),
+// the shock tube's wall reverses the whole momentum (example/shock/main.cpp:419-433).
+__device__ __forceinline__ void apply_particle_bc(const Geom& g, double& x, double& y, double& z, double& ux,
+                                                  double& uy, double& uz)
+{
+  if (!g.any_particle_bc)
+    return;
+  double* pos[3] = {&z, &y, &x};
+  double* mom[3] = {&uz, &uy, &ux};
+#pragma unroll
+  for (int axis = 0; axis < 3; axis++) {
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const int kind = g.bc_kind[axis][side];
+      if (kind != PICNIX_BC_CONDUCTING && kind != PICNIX_BC_WALL)
+        continue;
+      const double lim = g.glim[axis][side];
+      const bool   out = side == 0 ? *pos[axis] < lim : *pos[axis] >= lim;
+      if (out) {
+        *pos[axis] = -*pos[axis] + 2 * lim;
+        if (kind == PICNIX_BC_CONDUCTING) {
+          *mom[axis] = -*mom[axis];
+        } else {
+          ux = -ux;
+          uy = -uy;
+          uz = -uz;
+        }
+      }
+    }
+  }
 }
 
 //

@@ -850,6 +850,7 @@ bool row_geometry_applies(const picnix_arena* a)
 bool row_kernel_applies(const picnix_arena* a)
 {
   return row_geometry_applies(a) && a->pindex_valid && !a->force_generic;
+  // (physical boundary conditions: handled by rowpush.cu; the round-1 kernel is never selected with them)
 }
 
 // rowpush.cu: the second formulation (merged species stream, cell-anchored interpolation, 2-D register
@@ -867,7 +868,7 @@ int launch_deposit_rows(picnix_arena* a, int c0, int cn, double delt)
 
 int launch_row_fused(picnix_arena* a, int c0, int cn, double delt)
 {
-  if (a->row_version >= 2 && !a->deposit_mma && row_push_applies(a))
+  if ((a->row_version >= 2 || a->any_bc) && !a->deposit_mma && row_push_applies(a))
     return launch_row_fused_v2(a, c0, cn, delt);
   return launch_row_kernel<true>(a, c0, cn, delt);
 }

@@ -362,6 +362,7 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
         y1 = y0;
         z1 = z0;
         push_position_fast(x1, y1, z1, ux, uy, uz, rc.rc, delt);
+        apply_particle_bc(g, x1, y1, z1, ux, uy, uz);
         double* xo = PERM ? d.xv : d.xu; // i is the SORTED slot: in place, or the other buffer
         xo[0 * d.pcap + i] = x1;
         xo[1 * d.pcap + i] = y1;

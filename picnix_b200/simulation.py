@@ -96,6 +96,22 @@ class CudaSim:
         self._check(self.lib.picnix_cuda_get_counters(self.h, C.byref(launches), C.byref(pushes)))
         return launches.value, pushes.value
 
+    def set_boundary_condition(self, axis, side, kind, values=None):
+        """Physical boundary of one face (axis 0 = z, 1 = y, 2 = x; side 0 = lower, 1 = upper): the device
+        version of the set_boundary_field / set_boundary_particle hooks of the reference's examples."""
+        vals = None
+        if values is not None:
+            self._bc_values = np.ascontiguousarray(values, dtype=np.float64)
+            vals = self._bc_values.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.picnix_cuda_set_boundary_condition(self.h, axis, side, kind, vals))
+
+    def inject_particles(self, ic, isp, xu):
+        """PicChunk::inject_particle: append host-generated particles (between boundary_begin and
+        boundary_end of the particle exchange)."""
+        self.commit()
+        xu = np.ascontiguousarray(xu, dtype=np.float64).reshape(-1, 7)
+        self._check(self.lib.picnix_cuda_inject_particles(self.h, ic, isp, xu.reshape(-1), xu.shape[0]))
+
     def growth_stats(self):
         """(segment re-layouts, migrants delivered one step late) since the arena was created."""
         regrows, late = C.c_int64(), C.c_int64()
