@@ -243,6 +243,8 @@ class DistributedSim(CudaSim):
         for key, value in self._options.items():
             if key != "async_migration":
                 new.set_option(key, value)
+        for axis, side, kind, values in self._bcs:
+            new.set_boundary_condition(axis, side, kind, values)
         new.set_capacity(_capacities(np_all[new_boundary[self.rank]:new_boundary[self.rank + 1]],
                                      self.cfg.buffer_ratio))
         for isp, (q, m) in self._species.items():

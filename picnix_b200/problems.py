@@ -94,5 +94,74 @@ def setup_uniform_plasma(sim, ndims, cdims, species, ppc, delh=1.0, E0=(0, 0, 0)
         sim.finalize_setup()
 
 
+def harris_parameters(cc=1.0, sigma=0.0625, mime=25.0, tite=5.0, lcs=2.5, ncs=50, nbg=10):
+    """Derived quantities of the Harris current sheet of example/mrx/main.cpp:21-42."""
+    b0 = np.sqrt(sigma)
+    qe, qi = -1.0 / ncs, +1.0 / ncs
+    me = abs(qe)
+    mi = me * mime
+    vdi = -cc * b0 / (qi * ncs * lcs) / (1 + tite) * tite
+    vde = +cc * b0 / (qi * ncs * lcs) / (1 + tite) * 1.0
+    vti = np.sqrt(0.5 * b0 * b0 / (ncs * mi) / (1 + tite) * tite)
+    vte = np.sqrt(0.5 * b0 * b0 / (ncs * me) / (1 + tite) * 1.0)
+    return dict(b0=b0, q=(qe, qi), m=(me, mi), vd=(vde, vdi), vt=(vte, vti))
+
+
+def setup_harris_sheet(sim, ndims, cdims, delh=0.2, lcs=2.5, ncs=50, nbg=10, sigma=0.0625, mime=25.0, tite=5.0,
+                       bg=0.0, db=0.1, seed=0, chunk_id_begin=0, finalize=True):
+    """2-D Harris current sheet between conducting walls in y: the initial condition of example/mrx
+    (main.cpp:17-181; cc = 1, two species, phi = 0), with numpy's generator instead of std::mt19937_64.
+    The density is far from uniform -- chunks inside the sheet hold (nbg + ncs tanh-profile) particles per
+    cell, the others nbg -- which is what the load balancer is for.  The arena must have been created with
+    periodic = (1, 0, 1) and PICNIX_BC_CONDUCTING on both y faces."""
+    hp = harris_parameters(1.0, sigma, mime, tite, lcs, ncs, nbg)
+    dims = chunk_dims(ndims, cdims)
+    _, coord = sim.chunkmap()
+    for isp in range(2):
+        sim.set_species(isp, hp["q"][isp], hp["m"][isp])
+    nb = sim.nb
+    Mz, My, Mx = sim.shape
+    xcs, ycs = 0.5 * ndims[2] * delh, 0.5 * ndims[1] * delh
+    numcell = dims[0] * dims[1] * dims[2]
+    for ic in range(sim.nchunk):
+        gid = chunk_id_begin + ic
+        cx, cy, cz = (int(v) for v in coord[gid])
+        x0, y0, z0 = cx * dims[2] * delh, cy * dims[1] * delh, cz * dims[0] * delh
+        # fields on the whole padded array (main.cpp:56-84)
+        xi = x0 + (np.arange(Mx) - nb + 0.5) * delh - xcs
+        yi = y0 + (np.arange(My) - nb + 0.5) * delh - ycs
+        X, Y = np.meshgrid(xi, yi, indexing="xy")          # [My, Mx]
+        az = lambda xx, yy: 2 * db * lcs * np.exp(-(xx * xx + yy * yy) / (4 * lcs * lcs))
+        dbx = hp["b0"] * (+(az(X, Y) - az(X, Y - delh)) / delh)
+        dby = hp["b0"] * (-(az(X, Y) - az(X - delh, Y)) / delh)
+        uf = np.zeros((Mz, My, Mx, 6))
+        uf[..., 3] = dbx + hp["b0"] * np.tanh(Y / lcs)
+        uf[..., 4] = dby
+        uf[..., 5] = hp["b0"] * bg
+        sim.set_field(ic, FIELD_UF, uf)
+        # particles (main.cpp:101-176): background + current-sheet population, same positions for both species
+        rng = np.random.default_rng(seed * 1000003 + gid)
+        ymin, ymax = (y0 - ycs) / lcs, (y0 + dims[1] * delh - ycs) / lcs
+        rbg = numcell * nbg
+        rcs = numcell * ncs * (np.tanh(ymax) - np.tanh(ymin)) / (ymax - ymin)
+        mp = int(rbg + rcs)
+        x = rng.random(mp) * dims[2] * delh + x0
+        z = rng.random(mp) * dims[0] * delh + z0
+        sheet = rng.random(mp) < rcs / (rcs + rbg)
+        r = rng.random(mp)
+        y = np.where(sheet, ycs + lcs * np.arctanh(np.tanh(ymin) + r * (np.tanh(ymax) - np.tanh(ymin))),
+                     rng.random(mp) * dims[1] * delh + y0)
+        y = np.clip(y, y0, np.nextafter(y0 + dims[1] * delh, y0))
+        for isp in range(2):
+            xu = np.zeros((mp, 7))
+            xu[:, 0], xu[:, 1], xu[:, 2] = x, y, z
+            xu[:, 3:6] = rng.normal(size=(mp, 3)) * hp["vt"][isp]
+            xu[:, 5] += np.where(sheet, hp["vd"][isp], 0.0)
+            xu[:, 6] = (np.int64(mp) * 4 * gid + np.int64(mp) * isp + np.arange(mp, dtype=np.int64)).view(np.float64)
+            sim.set_particles(ic, isp, xu)
+    if finalize:
+        sim.finalize_setup()
+
+
 def total_particles(sim):
     return int(sum(sim.get_np(ic, isp) for ic in range(sim.nchunk) for isp in range(sim.Ns)))

@@ -60,6 +60,7 @@ class CudaSim:
         self._species = {}
         self._stream_ptr = None  # the arena owns its stream until set_stream() is called
         self._options = {}       # set_option history: carried over when the arena is rebuilt (rebalance)
+        self._bcs = []           # set_boundary_condition history, likewise
         self._ctor = dict(ndims=tuple(ndims), cdims=tuple(cdims), Ns=Ns, cc=cc, delh=delh, order=order,
                           pusher=pusher, interp=interp, periodic=tuple(periodic), friedman=friedman,
                           buffer_ratio=buffer_ratio)
@@ -104,6 +105,7 @@ class CudaSim:
             self._bc_values = np.ascontiguousarray(values, dtype=np.float64)
             vals = self._bc_values.ctypes.data_as(C.c_void_p)
         self._check(self.lib.picnix_cuda_set_boundary_condition(self.h, axis, side, kind, vals))
+        self._bcs.append((axis, side, kind, None if values is None else list(values)))
 
     def inject_particles(self, ic, isp, xu):
         """PicChunk::inject_particle: append host-generated particles (between boundary_begin and
