@@ -334,7 +334,8 @@ static int build_decomposition(picnix_arena* a, const int32_t* boundary)
 
     // Chunk::set_coordinate with the offsets of nix/application.cpp:291-300
     for (int i = 0; i < 3; i++) {
-      int    offset = cc3[i] * c.ndims[i] / c.cdims[i];
+      // = cc * ndims / cdims of the reference, without its 32-bit overflow for cc * ndims >= 2^31
+      int    offset = cc3[i] * g.dims[i];
       double lo     = offset * g.del[i];
       double hi     = offset * g.del[i] + g.dims[i] * g.del[i];
       clim[(size_t)ic * 6 + 2 * i + 0] = lo;

@@ -57,6 +57,9 @@ class Transport:
         self.view = cuda_view if device_buffers else host_view
         self.device = "cuda" if device_buffers else "cpu"
         self.peers = sim.peers() if world > 1 else []
+        # transfers overlap the kernels enqueued between start() and finish(); PICNIX_OVERLAP=0 restores
+        # the strictly serial pack -> transfer -> unpack of round 1
+        self.overlap = os.environ.get("PICNIX_OVERLAP", "1") != "0" and device_buffers
 
     def _shares_stream(self):
         """True when the arena enqueues on the stream torch (and therefore NCCL) orders against."""
@@ -66,11 +69,13 @@ class Transport:
 
         return getattr(self.sim, "_stream_ptr", None) == torch.cuda.current_stream().cuda_stream
 
-    def _exchange(self, pairs):
+    def _issue(self, pairs):
+        """Enqueue one group of sends / receives.  NCCL runs on its own stream, ordered after everything
+        enqueued on the current stream so far (the pack kernels); kernels enqueued afterwards overlap the
+        transfer until _complete() makes the current stream wait for it."""
         import torch.distributed as dist
 
-        shared = self._shares_stream()
-        if not shared:
+        if not self._shares_stream():
             # the arena packs on its own stream: NCCL must not read the buffers before that is done
             self.sim.synchronize()
         ops = []
@@ -79,14 +84,41 @@ class Transport:
                 ops.append(dist.P2POp(dist.irecv, recv, peer))
             if send.numel() > 0:
                 ops.append(dist.P2POp(dist.isend, send, peer))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        if not shared:
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def _complete(self, reqs):
+        for req in reqs:
+            req.wait()
+        if reqs and not self._shares_stream():
             # ... and the arena must not unpack before the data has landed
             import torch
 
             torch.cuda.current_stream().synchronize()
+
+    def _exchange(self, pairs):
+        self._complete(self._issue(pairs))
+
+    def start(self, mode):
+        """Non-blocking half of move(): after boundary_begin(mode), start the transfer and return a
+        ticket for finish().  The reference does the same with MPI_Isend / MPI_Irecv in
+        Chunk::begin_bc_exchange (nix/chunk.hpp:464-524) and goes on computing
+        (pic/pic_application.cpp:242-251)."""
+        if not self.peers:
+            return []
+        if mode == MODE_PARTICLE:
+            bufs = [self.sim.comm_buffer(mode, i) for i in range(len(self.peers))]
+            if any(b[3] == 0 for b in bufs):
+                self.move(mode)  # synchronous count exchange (first steps): nothing left to overlap
+                return []
+        pairs = []
+        for i, peer in enumerate(self.peers):
+            sp, sb, rp, rb = self.sim.comm_buffer(mode, i)
+            pairs.append((peer, self.view(sp, sb), self.view(rp, rb)))
+        return self._issue(pairs)
+
+    def finish(self, ticket):
+        """Before boundary_end(mode): the current stream waits for the transfer started by start()."""
+        self._complete(ticket)
 
     def move(self, mode):
         """Between boundary_begin(mode) and boundary_end(mode): send -> peer's recv buffer."""
@@ -122,22 +154,31 @@ def step_phases(sim, transport, dt, kernel_events=None):
     step; phase B: finish J, E step, start the E/B exchange; phases C-E: particles arrive (wrap,
     count, sort), fields arrive.
     """
+    overlap = hasattr(transport, "start") and getattr(transport, "overlap", True)
+    start = transport.start if overlap else (lambda mode: transport.move(mode))
+    finish = transport.finish if overlap else (lambda ticket: None)
+
     sim.push_bfd(0.5 * dt)
     if kernel_events is not None:
         kernel_events[0].record()
     sim.push_deposit_fused(dt)
     if kernel_events is not None:
         kernel_events[1].record()
+    # the J and particle transfers run under the second B half step, the J unpack and the E step; the
+    # E/B transfer under the particle unpack and the sort (pic/pic_application.cpp:242-251)
     sim.boundary_begin(MODE_CUR)
-    transport.move(MODE_CUR)
+    t_cur = start(MODE_CUR)
     sim.boundary_begin(MODE_PARTICLE)
-    transport.move(MODE_PARTICLE)
+    t_par = start(MODE_PARTICLE)
     sim.push_bfd(0.5 * dt)
+    finish(t_cur)
     sim.boundary_end(MODE_CUR)
     sim.push_efd(dt)
     sim.boundary_begin(MODE_EMF)
-    transport.move(MODE_EMF)
+    t_emf = start(MODE_EMF)
+    finish(t_par)
     sim.boundary_end(MODE_PARTICLE)
+    finish(t_emf)
     sim.boundary_end(MODE_EMF)
 
 
