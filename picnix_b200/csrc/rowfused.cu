@@ -840,9 +840,15 @@ int launch_row_kernel(picnix_arena* a, int c0, int cn, double delt)
 // The row-owner kernel needs 3-D, 2nd-order shapes, rows that split into RX-cell segments and
 // WARPS-row groups, and a pindex that describes the current particle order (set by the sort,
 // cleared by uploads).
+bool row_push2d_geometry(const picnix_arena* a); // rowpush2d.cu: the 2-D variant
+int  launch_deposit_rows_2d(picnix_arena* a, int c0, int cn, double delt);
+int  launch_row_fused_2d(picnix_arena* a, int c0, int cn, double delt);
+
 bool row_geometry_applies(const picnix_arena* a)
 {
   const Geom& g = a->g;
+  if (row_push2d_geometry(a))
+    return true;
   return g.dimension == 3 && g.order == 2 && (g.dims[2] % rowdep::RX) == 0 &&
          (g.dims[1] % rowdep::WARPS) == 0;
 }
@@ -861,6 +867,8 @@ int  launch_row_fused_v2(picnix_arena* a, int c0, int cn, double delt);
 
 int launch_deposit_rows(picnix_arena* a, int c0, int cn, double delt)
 {
+  if (a->g.dimension == 2)
+    return launch_deposit_rows_2d(a, c0, cn, delt);
   if (a->row_version >= 2 && !a->deposit_mma && row_push_applies(a))
     return launch_deposit_rows_v2(a, c0, cn, delt);
   return launch_row_kernel<false>(a, c0, cn, delt);
@@ -868,6 +876,8 @@ int launch_deposit_rows(picnix_arena* a, int c0, int cn, double delt)
 
 int launch_row_fused(picnix_arena* a, int c0, int cn, double delt)
 {
+  if (a->g.dimension == 2)
+    return launch_row_fused_2d(a, c0, cn, delt);
   if ((a->row_version >= 2 || a->any_bc) && !a->deposit_mma && row_push_applies(a))
     return launch_row_fused_v2(a, c0, cn, delt);
   return launch_row_kernel<true>(a, c0, cn, delt);

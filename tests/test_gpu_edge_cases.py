@@ -100,6 +100,42 @@ def test_tiled_kernel_variants_relativistic_multistep(pusher, interp):
     assert same and dx < 1e-11 and du < 1e-10
 
 
+def test_tiled_2d_kernel_far_movers_and_phases():
+    """The 2-D tiled kernel (rowpush2d.cu): one fused push + deposit against the reference's separate
+    calls, with a time step so large that many particles cross more than one cell (far-mover list)."""
+    ref, gpu = make_pair((1, 32, 32), (1, 2, 2), problems.THERMAL_SPECIES, (8, 8), 10.0)
+    dt = 0.9
+    ref.push_velocity(dt)
+    ref.push_position(dt)
+    ref.deposit_current(dt)
+    gpu.push_deposit_fused(dt)
+    dx, du, same = particle_err(gpu, ref, scale_x=32.0, scale_u=10.0)
+    assert same and dx < 1e-14 and du < 1e-13
+    assert keys_equal(gpu, ref)
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-12
+    # the tiled deposit-only path (separate phases with a valid pindex)
+    gpu.deposit_current(dt)
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-12
+
+
+@pytest.mark.parametrize("pusher,interp", [(0, 0), (0, 1), (1, 0), (2, 1)])
+def test_tiled_2d_kernel_variants_relativistic_multistep(pusher, interp):
+    """Pushers and WT interpolation through the tiled 2-D kernel at a relativistic temperature, three
+    species (the merged particle stream holds up to four), ragged segments, several steps."""
+    species = [dict(qm=-1.0, ro=1.0, vt=1.0), dict(qm=+0.1, ro=10.0, vt=0.3), dict(qm=-0.5, ro=0.5, vt=0.6)]
+    ref, gpu = make_pair((1, 32, 48), (1, 2, 3), species, (8, 5, 3), 1.0, pusher=pusher, interp=interp,
+                         B0=(0.5, 0.2, 0.3), thin=lambda ic, isp, n: n if (ic + isp) % 3 else n // 3)
+    dt = 0.4
+    ref.step(dt, 8)
+    gpu.step(dt, 8)
+    gpu.synchronize()
+    assert counts_equal(gpu, ref)
+    assert field_err(gpu, ref, FIELD_UF) < 1e-10
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-10
+    dx, du, same = particle_err(gpu, ref, scale_x=48.0, scale_u=1.0)
+    assert same and dx < 1e-11 and du < 1e-10
+
+
 def make_cherenkov_pair(ndims, cdims, nppc=16, u0=0.1, vt=0.1, delh=0.1, cc=1.0, order=2, seed=9):
     """example/cherenkov (main.cpp:31-160, config.toml): pair plasma (mime = 1) drifting with u0 along
     x, cell size delh = 0.1 (NOT 1), cc = 1, wp = 1: me = 1/nppc, qe = -wp/nppc*sqrt(gamma)."""
