@@ -2,6 +2,13 @@
 """bench.py -- particle-pushes/s of the PIC-NIX per-timestep hot path on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload thermal3d|twostream|cherenkov]
+
+--workload picks one of BASELINE.json's configurations; the default (thermal3d, described next) is the
+one the headline metric is quoted on.  twostream (example/beam/twostream: 1-D, three species) and
+cherenkov (example/cherenkov: 2-D drifting pair plasma) run in their NATIVE dimension, scaled up in
+extent until they fill a GPU, everything else as shipped in their config.toml; they go through the same
+timing, parity pre-check, e2e, roofline and reference arm.
 
 Workload (BASELINE.json configs[1], SURVEY.md §8d "T3D"): 3-D uniform thermal plasma, per GPU
 128x128x128 cells in 16^3-cell chunks (512 chunks), 2 species x 32 particles per cell = 64 ppc
@@ -38,11 +45,73 @@ sys.path.insert(0, ROOT)
 METRIC = "particle-pushes/sec/GPU (push+deposit+sort), 3D thermal plasma 64 ppc order 2"
 UNIT = "particle-steps/s"
 
-# workload constants
-CC, DELT, DELH, BX = 10.0, 0.05, 1.0, 5.0
 ORDER, PUSHER, INTERP = 2, 0, 0
-CHUNK = 16
-PPC = (32, 32)
+CHERENKOV_SPECIES = [dict(qm=-1.0, ro=1.0, vt=0.1, drift=(0.1, 0.0, 0.0)),
+                     dict(qm=+1.0, ro=1.0, vt=0.1, drift=(0.1, 0.0, 0.0))]
+
+
+class Workload:
+    """One BASELINE.json configuration: per-GPU extent (nz, ny, nx), chunk shape in cells, species,
+    particles per cell, constants of its config.toml; `sample` / `parity` are the extents of the
+    bounded CPU sample and of the parity pre-check (per rank)."""
+
+    def __init__(self, name, args):
+        from picnix_b200 import problems
+
+        self.name = name
+        if name == "thermal3d":    # SURVEY.md 8d "T3D": example/thermal with Nz, Ny > 1
+            n, r, q = args.cells or 128, args.ref_cells or 64, args.parity_cells or 32
+            p = args.ppc or 32
+            self.dims, self.chunk, self.sample, self.parity = (n, n, n), (16, 16, 16), (r, r, r), (q, q, q)
+            self.species, self.ppc = problems.THERMAL_SPECIES, (p, p)
+            self.cc, self.delt, self.delh, self.B0 = 10.0, 0.05, 1.0, (5.0, 0.0, 0.0)
+            self.metric = METRIC
+            self.label = (f"thermal-3D (example/thermal with Nz,Ny>1): {n}^3 cells per GPU in 16^3 chunks, "
+                          f"2 species x {p} ppc, order {ORDER}, Boris, MC, cc=10.0, delt=0.05, Bx=5.0, periodic")
+        elif name == "twostream":  # example/beam/twostream/config.toml: 8-cell chunks, 16+16+32 ppc
+            n, r, q = args.cells or (1 << 18), args.ref_cells or (1 << 15), args.parity_cells or 256
+            self.dims, self.chunk, self.sample, self.parity = (1, 1, n), (1, 1, 8), (1, 1, r), (1, 1, q)
+            self.species, self.ppc = problems.TWOSTREAM_SPECIES, (16, 16, 32)
+            self.cc, self.delt, self.delh, self.B0 = 50.0, 0.01, 1.0, (10.0, 0.0, 0.0)
+            self.metric = "particle-pushes/sec/GPU (push+deposit+sort), 1D two-stream 64 ppc order 2"
+            self.label = (f"two-stream 1-D (example/beam/twostream/config.toml): Nx={n} per GPU in 8-cell chunks, "
+                          f"3 species 16+16+32 ppc, order {ORDER}, Boris, MC, cc=50, delt=0.01, Bx=10, periodic")
+        elif name == "cherenkov":  # example/cherenkov/config.toml: 16^2 chunks, 2 x 32 ppc
+            n, r, q = args.cells or 1024, args.ref_cells or 512, args.parity_cells or 64
+            self.dims, self.chunk, self.sample, self.parity = (1, n, n), (1, 16, 16), (1, r, r), (1, q, q)
+            self.species, self.ppc = CHERENKOV_SPECIES, (32, 32)
+            self.cc, self.delt, self.delh, self.B0 = 1.0, 0.05, 0.1, (0.0, 0.0, 0.0)
+            self.metric = "particle-pushes/sec/GPU (push+deposit+sort), 2D drifting pair plasma 64 ppc order 2"
+            self.label = (f"cherenkov 2-D (example/cherenkov/config.toml): {n}^2 cells per GPU in 16^2 chunks, "
+                          f"2 species x 32 ppc, order {ORDER}, Boris, MC, cc=1, delt=0.05, delh=0.1, u0=0.1, periodic")
+        else:
+            raise SystemExit(f"unknown workload {name}")
+        self.Ns = len(self.species)
+
+    def layout(self, ngpu):
+        """Arrangement of the per-GPU blocks along the dimensions the workload has (x fastest)."""
+        ndim = sum(1 for n in self.dims if n > 1)
+        lay = {1: {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 1, 4), 8: (1, 1, 8)},
+               2: {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)},
+               3: {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}}
+        return lay[ndim][ngpu]
+
+    def box(self, per_rank, ngpu=1):
+        ndims = tuple(n * l for n, l in zip(per_rank, self.layout(ngpu)))
+        cdims = tuple(n // c for n, c in zip(ndims, self.chunk))
+        return ndims, cdims
+
+    def sim_kwargs(self):
+        return dict(Ns=self.Ns, cc=self.cc, delh=self.delh, order=ORDER, pusher=PUSHER, interp=INTERP)
+
+    def setup(self, sim, ndims, cdims, **kw):
+        from picnix_b200 import problems
+
+        problems.setup_uniform_plasma(sim, ndims, cdims, self.species, self.ppc, delh=self.delh, B0=self.B0, **kw)
+
+    @staticmethod
+    def shape_str(dims):
+        return "x".join(str(n) for n in dims if n > 1) or "1"
 
 # algorithmic bytes (DESIGN.md "Kernels and rooflines")
 BYTES_PUSH_PER_PARTICLE = 56 + 56 + 4 + 4      # fused push+deposit: read xu (+4 B permutation), write, write key
@@ -57,15 +126,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)    # warm-up 10, time >= 50 steps
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cells", type=int, default=128, help="cells per GPU per dimension")
-    ap.add_argument("--ppc", type=int, default=32, help="particles per cell per species")
+    ap.add_argument("--workload", default="thermal3d", choices=["thermal3d", "twostream", "cherenkov"])
+    ap.add_argument("--cells", type=int, default=0, help="cells per GPU per (non-trivial) dimension; 0: the workload's")
+    ap.add_argument("--ppc", type=int, default=0, help="particles per cell per species (thermal3d only)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--ref-cells", type=int, default=64, help="cells per dimension of the CPU sample")
+    ap.add_argument("--ref-cells", type=int, default=0, help="cells per dimension of the CPU sample; 0: the workload's")
     ap.add_argument("--ref-steps", type=int, default=0, help="override steps of the reference arm")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed N>1 parity pre-check")
-    ap.add_argument("--parity-cells", type=int, default=32, help="cells per rank per dimension of the pre-check")
+    ap.add_argument("--parity-cells", type=int, default=0, help="cells per rank per dimension of the pre-check")
     return ap.parse_args()
 
 
@@ -161,28 +231,26 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def run_reference(cells, ppc, steps, warmup):
+def run_reference(wl, steps, warmup):
     from oracle import ref_backend
     from picnix_b200 import problems
 
-    ndims = (cells, cells, cells)
-    cdims = tuple(n // CHUNK for n in ndims)
-    sim = ref_backend.RefSim(ndims, cdims, Ns=2, cc=CC, delh=DELH, order=ORDER, pusher=PUSHER, interp=INTERP,
-                             vector_mode=1, nthread=host_threads())
-    problems.setup_uniform_plasma(sim, ndims, cdims, problems.THERMAL_SPECIES, (ppc, ppc), delh=DELH,
-                                  B0=(BX, 0.0, 0.0), seed=1)
+    ndims, cdims = wl.box(wl.sample)
+    sim = ref_backend.RefSim(ndims, cdims, vector_mode=1, nthread=host_threads(), **wl.sim_kwargs())
+    wl.setup(sim, ndims, cdims, seed=1)
     npart = problems.total_particles(sim)
-    sim.step(DELT, warmup)
+    sim.step(wl.delt, warmup)
     t0 = time.perf_counter()
-    sim.step(DELT, steps)
+    sim.step(wl.delt, steps)
     elapsed = time.perf_counter() - t0
     lib = os.path.basename(ref_backend.library_path())
     return {
         "value": npart * steps / elapsed,
         "ms_per_step": 1e3 * elapsed / steps,
         "cores": sim.nthread,
-        "sample": f"{cells}^3 cells in {CHUNK}^3 chunks ({sim.nchunk} chunks), {2 * ppc} ppc, {npart} particles, "
-                  f"{steps} steps after {warmup} warm-up; reference 'vector' kernels + OpenMP over chunks, {lib}",
+        "sample": f"{wl.shape_str(wl.sample)} cells in {wl.shape_str(wl.chunk)} chunks ({sim.nchunk} chunks), "
+                  f"{sum(wl.ppc)} ppc, {npart} particles, {steps} steps after {warmup} warm-up; reference 'vector' "
+                  f"kernels + OpenMP over chunks, {lib}",
         "particles": npart,
     }
 
@@ -194,15 +262,16 @@ def reference_main(args, rank, world):
     # (ref_cells^3 cells of the same plasma: the CPU cost per particle does not depend on the box size)
     steps = args.ref_steps if args.ref_steps > 0 else args.steps
     warmup = args.warmup
-    res = run_reference(args.ref_cells, args.ppc, steps, warmup)
-    cfg = workload_config(args, args.gpus)
-    cfg["workload"] += (f"; THIS ARM: CPU sample of {args.ref_cells}^3 cells of that plasma per step "
+    wl = Workload(args.workload, args)
+    res = run_reference(wl, steps, warmup)
+    cfg = workload_config(wl, args.gpus)
+    cfg["workload"] += (f"; THIS ARM: CPU sample of {wl.shape_str(wl.sample)} cells of that plasma per step "
                         f"({res['particles']} particles), {res['cores']} host threads")
-    cfg["sample_cells"] = args.ref_cells ** 3
+    cfg["sample_cells"] = int(np.prod(wl.sample))
     cfg["sample_particles"] = res["particles"]
     line = {
         "impl": "reference",
-        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "metric": wl.metric, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
@@ -214,24 +283,20 @@ def reference_main(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, ngpu):
+def workload_config(wl, ngpu):
+    ncell = int(np.prod(wl.dims))
     return {
-        "workload": f"thermal-3D (example/thermal with Nz,Ny>1): {args.cells}^3 cells per GPU in {CHUNK}^3 chunks, "
-                    f"2 species x {args.ppc} ppc, order {ORDER}, Boris, MC, cc={CC}, delt={DELT}, Bx={BX}, periodic",
-        "cells_per_gpu": args.cells ** 3, "chunks_per_gpu": (args.cells // CHUNK) ** 3,
-        "particles_per_gpu": args.cells ** 3 * 2 * args.ppc, "parallelism": f"chunk decomposition over {ngpu} GPU(s)",
-        "l2_policy": "inputs (15 GB of particles per GPU) are far larger than the 126 MB L2; no flush needed",
+        "workload": wl.label, "name": wl.name,
+        "cells_per_gpu": ncell, "chunks_per_gpu": ncell // int(np.prod(wl.chunk)),
+        "particles_per_gpu": ncell * sum(wl.ppc), "parallelism": f"chunk decomposition over {ngpu} GPU(s)",
+        "l2_policy": f"inputs ({ncell * sum(wl.ppc) * 112 / 1e9:.1f} GB of particles per GPU) are far larger than "
+                     "the 126 MB L2; no flush needed",
     }
 
 
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def gpu_layout(ngpu):
-    """Arrangement of the per-GPU blocks: 1,2,4,8 GPUs -> (1,1,1),(1,1,2),(1,2,2),(2,2,2)."""
-    return {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}[ngpu]
-
-
 def bind_to_gpu_numa_node(local_rank):
     """Run this rank (and first-touch its pinned host buffers) on the CPUs of the NUMA node its GPU
     hangs off, so that the host<->device copies of the e2e measurement do not cross sockets.
@@ -262,7 +327,7 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
-def parity_precheck(args, rank, world, nstep=10):
+def parity_precheck(wl, rank, world, nstep=10):
     """Untimed parity check of the very path the bench times (fused tiled push+deposit, lazy sort,
     halos and migration -- over NCCL when world > 1) at the headline chunk shape: parity_cells^3
     cells per rank in 16^3 chunks at the bench's ppc, `nstep` steps, every rank's chunks gathered on
@@ -274,23 +339,20 @@ def parity_precheck(args, rank, world, nstep=10):
     from picnix_b200 import capi, problems
     from picnix_b200.distributed import DistributedSim
 
-    lay = gpu_layout(world)
-    ndims = tuple(args.parity_cells * l for l in lay)
-    cdims = tuple(n // CHUNK for n in ndims)
-    kw = dict(Ns=2, cc=CC, delh=DELH, order=ORDER, pusher=PUSHER, interp=INTERP)
-    setup = dict(delh=DELH, B0=(BX, 0.0, 0.0), seed=5, perturb=0.01)
+    ndims, cdims = wl.box(wl.parity, world)
+    kw = wl.sim_kwargs()
+    setup = dict(seed=5, perturb=0.01 * max(max(np.abs(wl.B0)), 0.1))
     sim = DistributedSim(ndims, cdims, rank=rank, world=world, **kw)
     sim.set_stream(torch.cuda.current_stream().cuda_stream)
-    problems.setup_uniform_plasma(sim, ndims, cdims, problems.THERMAL_SPECIES, (args.ppc, args.ppc),
-                                  chunk_id_begin=sim.chunk_id_begin, **setup)
+    wl.setup(sim, ndims, cdims, chunk_id_begin=sim.chunk_id_begin, **setup)
     for _ in range(nstep):
-        sim.step_phases(DELT)
+        sim.step_phases(wl.delt)
     sim.synchronize()
     mine = {"begin": sim.chunk_id_begin,
             "uf": [sim.get_field(ic, capi.FIELD_UF) for ic in range(sim.nchunk)],
             "uj": [sim.get_field(ic, capi.FIELD_UJ) for ic in range(sim.nchunk)],
             "np": sim.get_np_all(),
-            "pindex": [[sim.get_pindex(ic, isp) for isp in range(2)] for ic in range(sim.nchunk)]}
+            "pindex": [[sim.get_pindex(ic, isp) for isp in range(wl.Ns)] for ic in range(sim.nchunk)]}
     sim.close()
     if world > 1:
         parts = [None] * world
@@ -307,8 +369,8 @@ def parity_precheck(args, rank, world, nstep=10):
         from oracle import port_backend
 
         ref, name = port_backend.PortSim(ndims, cdims, **kw), "C restatement (oracle/libpicnix_oracle.so)"
-    problems.setup_uniform_plasma(ref, ndims, cdims, problems.THERMAL_SPECIES, (args.ppc, args.ppc), **setup)
-    ref.step(DELT, nstep)
+    wl.setup(ref, ndims, cdims, **setup)
+    ref.step(wl.delt, nstep)
     err_f = err_j = 0.0
     counts = True
     nchunk = 0
@@ -323,10 +385,10 @@ def parity_precheck(args, rank, world, nstep=10):
                     err_f = max(err_f, e)
                 else:
                     err_j = max(err_j, e)
-            for isp in range(2):
+            for isp in range(wl.Ns):
                 counts = counts and int(part["np"][ic, isp]) == ref.get_np(gid, isp)
                 counts = counts and bool(np.array_equal(part["pindex"][ic][isp], ref.get_pindex(gid, isp)))
-    return {"oracle": name, "cells": list(ndims), "chunks": nchunk, "ppc": 2 * args.ppc, "steps": nstep,
+    return {"oracle": name, "cells": list(ndims), "chunks": nchunk, "ppc": sum(wl.ppc), "steps": nstep,
             "ranks": world, "max_rel_field_err": err_f, "max_rel_current_err": err_j, "counts_equal": counts,
             "tolerance": 1e-10, "ok": bool(counts and err_f < 1e-10 and err_j < 1e-10)}
 
@@ -350,24 +412,21 @@ def b200_main(args, rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    wl = Workload(args.workload, args)
     parity = None
     if not args.no_parity:
         try:
-            parity = parity_precheck(args, rank, world)
+            parity = parity_precheck(wl, rank, world)
         except Exception as exc:  # report, never hide: the line then says the check did not run
             parity = {"ok": False, "error": f"{type(exc).__name__}: {exc}"}
 
-    lay = gpu_layout(world)
-    ndims = tuple(args.cells * l for l in lay)
-    cdims = tuple(n // CHUNK for n in ndims)
-    sim = DistributedSim(ndims, cdims, Ns=2, cc=CC, delh=DELH, order=ORDER, pusher=PUSHER, interp=INTERP,
-                         rank=rank, world=world)
+    ndims, cdims = wl.box(wl.dims, world)
+    sim = DistributedSim(ndims, cdims, rank=rank, world=world, **wl.sim_kwargs())
     stream = torch.cuda.Stream()
     sim.set_stream(stream.cuda_stream)
-    problems.setup_uniform_plasma(sim, ndims, cdims, problems.THERMAL_SPECIES, (args.ppc, args.ppc), delh=DELH,
-                                  B0=(BX, 0.0, 0.0), seed=1, chunk_id_begin=sim.chunk_id_begin)
+    wl.setup(sim, ndims, cdims, seed=1, chunk_id_begin=sim.chunk_id_begin)
     np_local = int(sim.get_np_all().sum())
-    ncell_local = args.cells ** 3
+    ncell_local = int(np.prod(wl.dims))
 
     def barrier():
         torch.cuda.synchronize()
@@ -377,7 +436,7 @@ def b200_main(args, rank, world):
 
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
-            sim.step_phases(DELT)
+            sim.step_phases(wl.delt)
         barrier()
         launches0, _ = sim.counters()
         sampler = ClockSampler(local_rank)
@@ -388,7 +447,7 @@ def b200_main(args, rank, world):
                for _ in range(args.steps)]
         ev0.record(stream)
         for k in range(args.steps):
-            sim.step_phases(DELT, kernel_events=kev[k])
+            sim.step_phases(wl.delt, kernel_events=kev[k])
         ev1.record(stream)
         barrier()
         clocks = sampler.stop() if rank == 0 else None
@@ -442,7 +501,7 @@ def b200_main(args, rank, world):
     # arrays); max wall time over ranks, particles and bytes summed over ranks
     e2e = None
     if not args.no_e2e:
-        res = sim.measure_e2e(DELT, args.e2e_steps, barrier=barrier)
+        res = sim.measure_e2e(wl.delt, args.e2e_steps, barrier=barrier)
         te = torch.tensor([res["elapsed"], res["particles"], float(res["h2d"]), float(res["d2h"])],
                           dtype=torch.float64, device="cuda")
         if world > 1:
@@ -465,7 +524,7 @@ def b200_main(args, rank, world):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:  # the CPU baseline is timed at N=1 only
         try:
-            res = run_reference(args.ref_cells, args.ppc, 5, 1)
+            res = run_reference(wl, 5, 1)
             cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
                    "sample": res["sample"]}
         except Exception as exc:  # the reference binary is absent: say so instead of inventing a number
@@ -473,10 +532,10 @@ def b200_main(args, rank, world):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": workload_config(wl, world),
             "per_gpu": value / world,
             "particles_before_after": [np_total, np_after_total],
             "conservation": {"particles_conserved": np_total == np_after_total,

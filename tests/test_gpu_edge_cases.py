@@ -113,8 +113,12 @@ def test_tiled_2d_kernel_far_movers_and_phases():
     assert same and dx < 1e-14 and du < 1e-13
     assert keys_equal(gpu, ref)
     assert field_err(gpu, ref, FIELD_UJ) < 1e-12
-    # the tiled deposit-only path (separate phases with a valid pindex)
-    gpu.deposit_current(dt)
+    # the tiled deposit-only path: the reference's separate calls on a fresh pair (old position in xv)
+    ref, gpu = make_pair((1, 32, 32), (1, 2, 2), problems.THERMAL_SPECIES, (8, 8), 10.0)
+    for sim in (ref, gpu):
+        sim.push_velocity(dt)
+        sim.push_position(dt)
+        sim.deposit_current(dt)
     assert field_err(gpu, ref, FIELD_UJ) < 1e-12
 
 

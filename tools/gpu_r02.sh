@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU session: parity tests, short benches of both row kernels, ncu of the new one.
 # Usage (under gpurun, from the repo root):  bash tools/gpu_r02.sh <tag> [what...]
-#   what: tests tests1 bench bench1 benchfull benchref launches full sweep   (default: tests bench bench1 full)
+#   what: tests tests1 bench bench1 benchfull benchref benchwl launches full sweep   (default: tests bench bench1 full)
 set -u
 TAG=${1:-r02a}
 shift || true
@@ -41,6 +41,13 @@ if has benchref; then
   timeout 900 python bench.py --impl reference --steps 10 --warmup 3 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"
   cat "$OUT/bench_ref.json"
 fi
+if has benchwl; then
+  for w in ${WORKLOADS:-cherenkov twostream}; do
+    timeout 900 python bench.py --workload $w --steps 20 --warmup 5 ${BENCHWL_ARGS:---e2e-steps 2} > "$OUT/bench_$w.json" 2> "$OUT/bench_$w.err"
+    echo "bench exit $?" >> "$OUT/bench_$w.err"
+    cat "$OUT/bench_$w.json"; tail -2 "$OUT/bench_$w.err"
+  done
+fi
 if has launches; then
   timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -s ${LAUNCH_SKIP:-1030} -c 400 --csv \
     --log-file "$OUT/launches.csv" python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-parity > "$OUT/launches_run.log" 2>&1
@@ -50,7 +57,7 @@ fi
 if has full; then
   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNEL:-row_push_kernel}" \
     -s ${NCU_SKIP:-3} -c 1 -f -o "$OUT/prof_${NCU_NAME:-row_push}" \
-    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-parity > "$OUT/full_run.log" 2>&1
+    python bench.py ${NCU_BENCH_ARGS:-} --steps 2 --warmup 3 --no-e2e --no-cpu --no-parity > "$OUT/full_run.log" 2>&1
   ls -la "$OUT"
 fi
 if has sweep; then
