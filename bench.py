@@ -140,18 +140,20 @@ def parse_args():
 
 
 def ncu_traffic(np_local, ncell_local):
-    """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/row_kernel_traffic.json); None when the capture was taken on another workload size."""
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full captures
+    (profiles/row_kernel_traffic.json, newest first); None when no capture was taken on this workload size."""
     try:
         with open(os.path.join(ROOT, "profiles", "row_kernel_traffic.json")) as fp:
-            t = json.load(fp)
-        if t["particles_per_launch"] != np_local or t["cells_per_launch"] != ncell_local:
-            return None, None
-        pipes = {k: t[k] for k in ("lsu_data_pipe_pct_of_peak", "fp64_pipe_pct_of_peak", "issue_active_pct",
-                                   "dram_throughput_pct_of_peak", "warps_per_sm") if k in t}
-        return t["dram_bytes_read"] + t["dram_bytes_write"], pipes
+            caps = json.load(fp)["captures"]
+        for t in caps:
+            if t["particles_per_launch"] == np_local and t["cells_per_launch"] == ncell_local:
+                pipes = {k: t[k] for k in ("kernel", "source", "lsu_data_pipe_pct_of_peak", "fp64_pipe_pct_of_peak",
+                                           "issue_active_pct", "dram_throughput_pct_of_peak", "warps_per_sm",
+                                           "registers_per_thread") if k in t}
+                return t["dram_bytes_read"] + t["dram_bytes_write"], pipes
     except Exception:
-        return None, None
+        pass
+    return None, None
 
 
 def measured_peaks():
@@ -438,6 +440,7 @@ def b200_main(args, rank, world):
         for _ in range(args.warmup):
             sim.step_phases(wl.delt)
         barrier()
+        de_before = sim.get_diverror()  # residuals after warm-up: the timed region must not change them
         launches0, _ = sim.counters()
         sampler = ClockSampler(local_rank)
         if rank == 0:
@@ -461,8 +464,11 @@ def b200_main(args, rank, world):
     # chunk like PicChunk::get_diverror, worst chunk reported)
     de = sim.get_diverror()
     div_e_worst, div_b_worst = float(np.abs(de[:, 0]).max()), float(np.abs(de[:, 1]).max())
+    # Gauss's law is an initial condition the scheme preserves: what the timed steps may not do is change
+    # the residual (a non-neutral start, e.g. two-stream's independently placed ions, keeps its own)
+    div_e_drift = float(np.abs(de[:, 0] - de_before[:, 0]).max())
 
-    t = torch.tensor([elapsed_ms, float(np_local), float(np_after), kernel_ms, div_e_worst, div_b_worst],
+    t = torch.tensor([elapsed_ms, float(np_local), float(np_after), kernel_ms, div_e_worst, div_b_worst, div_e_drift],
                      dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
@@ -471,7 +477,7 @@ def b200_main(args, rank, world):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         elapsed_ms = float(tmax[0])
         kernel_ms = float(tmax[3])
-        div_e_worst, div_b_worst = float(tmax[4]), float(tmax[5])
+        div_e_worst, div_b_worst, div_e_drift = float(tmax[4]), float(tmax[5]), float(tmax[6])
         np_total = float(tsum[1])
         np_after_total = float(tsum[2])
     else:
@@ -488,7 +494,8 @@ def b200_main(args, rank, world):
     roofline = {
         "bound": "hbm", "kernel": "push_deposit_fused", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "limiter": "shared-memory data pipe (LSU wavefronts) and FP64 issue, not HBM: see ncu_pipes and DESIGN.md 3.1",
+        "limiter": "not HBM: shared-memory data pipe (LSU wavefronts), FP64 issue and instruction latency at 8-12 warps/SM; "
+                   "see ncu_pipes and DESIGN.md 3.1",
         "ncu_pipes": pipes,
         "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * args.steps / elapsed_ms,
         "algorithmic_bytes_per_launch": alg_bytes,
@@ -539,7 +546,8 @@ def b200_main(args, rank, world):
             "per_gpu": value / world,
             "particles_before_after": [np_total, np_after_total],
             "conservation": {"particles_conserved": np_total == np_after_total,
-                             "max_chunk_abs_sum_divE_minus_rho": div_e_worst, "max_chunk_abs_sum_divB": div_b_worst},
+                             "max_chunk_abs_sum_divE_minus_rho": div_e_worst, "max_chunk_abs_sum_divB": div_b_worst,
+                             "max_chunk_change_of_divE_minus_rho_over_timed_steps": div_e_drift},
             "parity_check": parity,
             "clocks": clocks,
             "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0,
