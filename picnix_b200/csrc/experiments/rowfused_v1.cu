@@ -1,4 +1,10 @@
 // -*- C++ -*-
+// NOT THE PRODUCT PATH.  Round-1 row-owner kernel and the FP64-MMA deposit experiment, kept buildable as
+// measured evidence (profiles/r01_row_kernel_ncu.txt, profiles/r01_row_mma_ncu.txt: the MMA deposit is
+// 1.74x slower) and as the tiled path for more than rowtile::MAXNS species.  Selected only
+// by set_option("row_kernel", 1) / set_option("deposit_mma", 1); the hot kernels are rowpush.cu (3-D)
+// and rowpush2d.cu (2-D), dispatched from rowdispatch.cu.
+//
 // Row-owner kernel (3-D, order 2): see rowdeposit.cuh for the scheme.
 //   FUSED = true : phase 1 interpolates the fields, pushes momentum and position, writes the new
 //                  state in place and produces the cell key + histogram (K1 + K2 in one pass over
@@ -837,50 +843,16 @@ int launch_row_kernel(picnix_arena* a, int c0, int cn, double delt)
 
 } // namespace
 
-// The row-owner kernel needs 3-D, 2nd-order shapes, rows that split into RX-cell segments and
-// WARPS-row groups, and a pindex that describes the current particle order (set by the sort,
-// cleared by uploads).
-bool row_push2d_geometry(const picnix_arena* a); // rowpush2d.cu: the 2-D variant
-int  launch_deposit_rows_2d(picnix_arena* a, int c0, int cn, double delt);
-int  launch_row_fused_2d(picnix_arena* a, int c0, int cn, double delt);
+int launch_row_kernel_v1(picnix_arena* a, int c0, int cn, double delt, bool fused)
+{
+  return fused ? launch_row_kernel<true>(a, c0, cn, delt) : launch_row_kernel<false>(a, c0, cn, delt);
+}
 
-bool row_geometry_applies(const picnix_arena* a)
+// v1 geometry: rows that split into RX-cell segments and WARPS-row groups
+bool row_v1_geometry(const picnix_arena* a)
 {
   const Geom& g = a->g;
-  if (row_push2d_geometry(a))
-    return true;
-  return g.dimension == 3 && g.order == 2 && (g.dims[2] % rowdep::RX) == 0 &&
-         (g.dims[1] % rowdep::WARPS) == 0;
-}
-
-bool row_kernel_applies(const picnix_arena* a)
-{
-  return row_geometry_applies(a) && a->pindex_valid && !a->force_generic;
-  // (physical boundary conditions: handled by rowpush.cu; the round-1 kernel is never selected with them)
-}
-
-// rowpush.cu: the second formulation (merged species stream, cell-anchored interpolation, 2-D register
-// tiles); option "row_kernel" = 1 selects the round-1 kernel of this file instead
-bool row_push_applies(const picnix_arena* a);
-int  launch_deposit_rows_v2(picnix_arena* a, int c0, int cn, double delt);
-int  launch_row_fused_v2(picnix_arena* a, int c0, int cn, double delt);
-
-int launch_deposit_rows(picnix_arena* a, int c0, int cn, double delt)
-{
-  if (a->g.dimension == 2)
-    return launch_deposit_rows_2d(a, c0, cn, delt);
-  if (a->row_version >= 2 && !a->deposit_mma && row_push_applies(a))
-    return launch_deposit_rows_v2(a, c0, cn, delt);
-  return launch_row_kernel<false>(a, c0, cn, delt);
-}
-
-int launch_row_fused(picnix_arena* a, int c0, int cn, double delt)
-{
-  if (a->g.dimension == 2)
-    return launch_row_fused_2d(a, c0, cn, delt);
-  if ((a->row_version >= 2 || a->any_bc) && !a->deposit_mma && row_push_applies(a))
-    return launch_row_fused_v2(a, c0, cn, delt);
-  return launch_row_kernel<true>(a, c0, cn, delt);
+  return g.dimension == 3 && g.order == 2 && (g.dims[2] % rowdep::RX) == 0 && (g.dims[1] % rowdep::WARPS) == 0;
 }
 
 } // namespace picnix

@@ -23,7 +23,7 @@ namespace picnix
 namespace
 {
 
-constexpr int MAXWELL_THREADS = 128;
+constexpr int MAXWELL_THREADS = 256; // cells per block (and threads)
 
 struct CellIndex {
   int     chunk, iz, iy, ix;
@@ -58,21 +58,94 @@ __device__ __forceinline__ CellIndex decode_cell(const Geom& g, int c0, int cn)
   return idx;
 }
 
-__device__ __forceinline__ double filtered(const double* __restrict__ uf,
-                                           const double* __restrict__ ff, int64_t cell, int k,
-                                           double A, double B, double C)
+// Shared-memory staging.  A thread owns one padded cell whose uf (48 B) and ff (72 B) records are 48 / 72 B
+// apart from its neighbour's: loading them thread by thread touches 12-18 cache lines per warp instruction
+// and the kernels end up bound by the L1 tag rate, not by HBM.  The cells of a block are contiguous in
+// memory (always in 3-D; inside one chunk's plane / row in 2-D / 1-D), so the block copies its whole range
+// with coalesced loads, works in shared memory, and writes the range back with coalesced stores.  Values
+// the kernel does not change are written back unchanged (bit-identical, nobody else writes them).
+// Neighbours inside the block's range (x-1 / x+1 always but for one thread, y-1 / y+1 mostly) are read
+// from the stage, the others from global memory.  Blocks that straddle a gap fall back to direct access.
+template <int Dim>
+__device__ __forceinline__ int64_t flat_cell(const Geom& g, int c0, int64_t t)
 {
-  // ff(.., 0, k) = A * uf(.., k) + B * ff(.., 1, k) + C * ff(.., 2, k)
-  return A * uf[cell * 6 + k] + B * ff[cell * 9 + 3 + k] + C * ff[cell * 9 + 6 + k];
+  const int     nx = g.M[2];
+  const int     ny = Dim >= 2 ? g.M[1] : 1;
+  const int     nz = Dim >= 3 ? g.M[0] : 1;
+  const int64_t per_chunk = (int64_t)nx * ny * nz;
+  const int     lc = (int)(t / per_chunk);
+  const int64_t r  = t - (int64_t)lc * per_chunk;
+  const int     jz = (int)(r / ((int64_t)nx * ny));
+  const int     r2 = (int)(r - (int64_t)jz * nx * ny);
+  const int     jy = r2 / nx;
+  const int     ix = r2 - jy * nx;
+  const int     iy = Dim >= 2 ? jy : g.Lb[1];
+  const int     iz = Dim >= 3 ? jz : g.Lb[0];
+  return (((int64_t)(c0 + lc) * g.M[0] + iz) * g.M[1] + iy) * g.M[2] + ix;
+}
+
+// first cell of the block's contiguous range, or -1 when the block must use direct access (block-uniform)
+template <int Dim>
+__device__ __forceinline__ int64_t block_range(const Geom& g, int c0, int cn)
+{
+  const int     nx = g.M[2];
+  const int     ny = Dim >= 2 ? g.M[1] : 1;
+  const int     nz = Dim >= 3 ? g.M[0] : 1;
+  const int64_t total = (int64_t)nx * ny * nz * cn;
+  const int64_t t0    = (int64_t)blockIdx.x * MAXWELL_THREADS;
+  if (t0 + MAXWELL_THREADS > total)
+    return -1;
+  const int64_t first = flat_cell<Dim>(g, c0, t0);
+  const int64_t last  = flat_cell<Dim>(g, c0, t0 + MAXWELL_THREADS - 1);
+  return last - first == MAXWELL_THREADS - 1 ? first : -1;
+}
+
+template <int W>
+__device__ __forceinline__ void stage_in(double* __restrict__ s, const double* __restrict__ gsrc, int64_t first)
+{
+#pragma unroll
+  for (int i = 0; i < W; i++)
+    s[i * MAXWELL_THREADS + threadIdx.x] = gsrc[first * W + i * MAXWELL_THREADS + threadIdx.x];
+}
+
+template <int W>
+__device__ __forceinline__ void stage_out(double* __restrict__ gdst, const double* __restrict__ s, int64_t first)
+{
+#pragma unroll
+  for (int i = 0; i < W; i++)
+    gdst[first * W + i * MAXWELL_THREADS + threadIdx.x] = s[i * MAXWELL_THREADS + threadIdx.x];
+}
+
+// record of `cell`: from the stage when it lies in the block's range
+template <int W>
+__device__ __forceinline__ const double* record(const double* s, const double* gsrc, int64_t first, int64_t cell)
+{
+  const int64_t li = cell - first;
+  return (first >= 0 && li >= 0 && li < MAXWELL_THREADS) ? s + li * W : gsrc + cell * W;
+}
+
+// ff(.., 0, k) = A * uf(.., k) + B * ff(.., 1, k) + C * ff(.., 2, k)
+__device__ __forceinline__ double filtered(const double* ufr, const double* ffr, int k, double A, double B, double C)
+{
+  return A * ufr[k] + B * ffr[3 + k] + C * ffr[6 + k];
 }
 
 template <int Dim>
 __global__ void __launch_bounds__(MAXWELL_THREADS)
 push_bfd_kernel(Geom g, DevPtrs d, int c0, int cn, double delt)
 {
+  __shared__ double s_uf[MAXWELL_THREADS * 6];
+  __shared__ double s_ff[MAXWELL_THREADS * 9];
+
+  const int64_t first = block_range<Dim>(g, c0, cn);
+  if (first >= 0) {
+    stage_in<6>(s_uf, d.uf, first);
+    stage_in<9>(s_ff, d.ff, first);
+    __syncthreads();
+  }
   CellIndex idx = decode_cell<Dim>(g, c0, cn);
   if (!idx.valid)
-    return;
+    return; // never in a staged block (its range is complete)
 
   const double theta = g.theta;
   const double A     = 1 + 0.5 * theta;
@@ -84,59 +157,77 @@ push_bfd_kernel(Geom g, DevPtrs d, int c0, int cn, double delt)
 
   const int64_t sx = 1, sy = g.M[2], sz = (int64_t)g.M[1] * g.M[2];
   const int64_t c  = idx.cell;
-  double*       uf = d.uf;
-  double*       ff = d.ff;
+  // own records (read and written), neighbour records (read only; E, ff1, ff2 are inputs of this kernel)
+  double*       ufc = first >= 0 ? s_uf + (c - first) * 6 : d.uf + c * 6;
+  double*       ffc = first >= 0 ? s_ff + (c - first) * 9 : d.ff + c * 9;
+  const double* ufx = record<6>(s_uf, d.uf, first, c - sx);
+  const double* ffx = record<9>(s_ff, d.ff, first, c - sx);
+  const double* ufy = record<6>(s_uf, d.uf, first, c - sy);
+  const double* ffy = record<9>(s_ff, d.ff, first, c - sy);
+  const double* ufz = d.uf + (c - sz) * 6; // a plane away: never in the block's range
+  const double* ffz = d.ff + (c - sz) * 9;
 
   // filtered E at this cell (stored) and at the -1 neighbours (recomputed, same expression)
-  double f0x = filtered(uf, ff, c, 0, A, B, C);
-  double f0y = filtered(uf, ff, c, 1, A, B, C);
-  double f0z = filtered(uf, ff, c, 2, A, B, C);
-  ff[c * 9 + 0] = f0x;
-  ff[c * 9 + 1] = f0y;
-  ff[c * 9 + 2] = f0z;
+  double f0x = filtered(ufc, ffc, 0, A, B, C);
+  double f0y = filtered(ufc, ffc, 1, A, B, C);
+  double f0z = filtered(ufc, ffc, 2, A, B, C);
 
   // lower bounds of the B loops are lb - Nb + 1 == 1 in the staggered directions
   const bool okx = idx.ix >= 1;
   const bool oky = Dim >= 2 ? idx.iy >= 1 : true;
   const bool okz = Dim >= 3 ? idx.iz >= 1 : true;
 
+  double bx = ufc[3], by = ufc[4], bz = ufc[5];
   if (Dim == 1) {
     if (okx) {
-      double fzx = filtered(uf, ff, c - sx, 2, A, B, C);
-      double fyx = filtered(uf, ff, c - sx, 1, A, B, C);
-      uf[c * 6 + 4] += (+cflx) * (f0z - fzx);
-      uf[c * 6 + 5] += (-cflx) * (f0y - fyx);
+      double fzx = filtered(ufx, ffx, 2, A, B, C);
+      double fyx = filtered(ufx, ffx, 1, A, B, C);
+      by += (+cflx) * (f0z - fzx);
+      bz += (-cflx) * (f0y - fyx);
     }
   } else if (Dim == 2) {
     if (oky) {
-      double fzy = filtered(uf, ff, c - sy, 2, A, B, C);
-      uf[c * 6 + 3] += (-cfly) * (f0z - fzy);
+      double fzy = filtered(ufy, ffy, 2, A, B, C);
+      bx += (-cfly) * (f0z - fzy);
     }
     if (okx) {
-      double fzx = filtered(uf, ff, c - sx, 2, A, B, C);
-      uf[c * 6 + 4] += (+cflx) * (f0z - fzx);
+      double fzx = filtered(ufx, ffx, 2, A, B, C);
+      by += (+cflx) * (f0z - fzx);
     }
     if (okx && oky) {
-      double fyx = filtered(uf, ff, c - sx, 1, A, B, C);
-      double fxy = filtered(uf, ff, c - sy, 0, A, B, C);
-      uf[c * 6 + 5] += (-cflx) * (f0y - fyx) + (+cfly) * (f0x - fxy);
+      double fyx = filtered(ufx, ffx, 1, A, B, C);
+      double fxy = filtered(ufy, ffy, 0, A, B, C);
+      bz += (-cflx) * (f0y - fyx) + (+cfly) * (f0x - fxy);
     }
   } else {
     if (okz && oky) {
-      double fzy = filtered(uf, ff, c - sy, 2, A, B, C);
-      double fyz = filtered(uf, ff, c - sz, 1, A, B, C);
-      uf[c * 6 + 3] += (-cfly) * (f0z - fzy) + (+cflz) * (f0y - fyz);
+      double fzy = filtered(ufy, ffy, 2, A, B, C);
+      double fyz = filtered(ufz, ffz, 1, A, B, C);
+      bx += (-cfly) * (f0z - fzy) + (+cflz) * (f0y - fyz);
     }
     if (okz && okx) {
-      double fxz = filtered(uf, ff, c - sz, 0, A, B, C);
-      double fzx = filtered(uf, ff, c - sx, 2, A, B, C);
-      uf[c * 6 + 4] += (-cflz) * (f0x - fxz) + (+cflx) * (f0z - fzx);
+      double fxz = filtered(ufz, ffz, 0, A, B, C);
+      double fzx = filtered(ufx, ffx, 2, A, B, C);
+      by += (-cflz) * (f0x - fxz) + (+cflx) * (f0z - fzx);
     }
     if (oky && okx) {
-      double fyx = filtered(uf, ff, c - sx, 1, A, B, C);
-      double fxy = filtered(uf, ff, c - sy, 0, A, B, C);
-      uf[c * 6 + 5] += (-cflx) * (f0y - fyx) + (+cfly) * (f0x - fxy);
+      double fyx = filtered(ufx, ffx, 1, A, B, C);
+      double fxy = filtered(ufy, ffy, 0, A, B, C);
+      bz += (-cflx) * (f0y - fyx) + (+cfly) * (f0x - fxy);
     }
+  }
+  // outputs: ff0 and B; in a staged block they go to the stage after every thread has read its inputs
+  // (ff0 and B are nobody's input here, so no barrier is needed before these stores)
+  ffc[0] = f0x;
+  ffc[1] = f0y;
+  ffc[2] = f0z;
+  ufc[3] = bx;
+  ufc[4] = by;
+  ufc[5] = bz;
+  if (first >= 0) {
+    __syncthreads();
+    stage_out<6>(d.uf, s_uf, first);
+    stage_out<9>(d.ff, s_ff, first);
   }
 }
 
@@ -144,6 +235,17 @@ template <int Dim>
 __global__ void __launch_bounds__(MAXWELL_THREADS)
 push_efd_kernel(Geom g, DevPtrs d, int c0, int cn, double delt)
 {
+  __shared__ double s_uf[MAXWELL_THREADS * 6];
+  __shared__ double s_ff[MAXWELL_THREADS * 9];
+  __shared__ double s_uj[MAXWELL_THREADS * 4];
+
+  const int64_t first = block_range<Dim>(g, c0, cn);
+  if (first >= 0) {
+    stage_in<6>(s_uf, d.uf, first);
+    stage_in<9>(s_ff, d.ff, first);
+    stage_in<4>(s_uj, d.uj, first);
+    __syncthreads();
+  }
   CellIndex idx = decode_cell<Dim>(g, c0, cn);
   if (!idx.valid)
     return;
@@ -155,56 +257,62 @@ push_efd_kernel(Geom g, DevPtrs d, int c0, int cn, double delt)
 
   const int64_t sx = 1, sy = g.M[2], sz = (int64_t)g.M[1] * g.M[2];
   const int64_t c  = idx.cell;
-  double*       uf = d.uf;
-  double*       ff = d.ff;
-  const double* uj = d.uj;
+  double*       ufc = first >= 0 ? s_uf + (c - first) * 6 : d.uf + c * 6;
+  double*       ffc = first >= 0 ? s_ff + (c - first) * 9 : d.ff + c * 9;
+  const double* ujc = first >= 0 ? s_uj + (c - first) * 4 : d.uj + c * 4;
+  // the +1 neighbours' B (an input of this kernel: nobody writes it)
+  const double* ufx = record<6>(s_uf, d.uf, first, c + sx);
+  const double* ufy = record<6>(s_uf, d.uf, first, c + sy);
+  const double* ufz = d.uf + (c + sz) * 6;
 
   // Friedman history shift first (uses E before the update)
-  double ex = uf[c * 6 + 0], ey = uf[c * 6 + 1], ez = uf[c * 6 + 2];
-  ff[c * 9 + 6] = ff[c * 9 + 3] + theta * ff[c * 9 + 6];
-  ff[c * 9 + 3] = ex;
-  ff[c * 9 + 7] = ff[c * 9 + 4] + theta * ff[c * 9 + 7];
-  ff[c * 9 + 4] = ey;
-  ff[c * 9 + 8] = ff[c * 9 + 5] + theta * ff[c * 9 + 8];
-  ff[c * 9 + 5] = ez;
+  double ex = ufc[0], ey = ufc[1], ez = ufc[2];
+  ffc[6] = ffc[3] + theta * ffc[6];
+  ffc[3] = ex;
+  ffc[7] = ffc[4] + theta * ffc[7];
+  ffc[4] = ey;
+  ffc[8] = ffc[5] + theta * ffc[8];
+  ffc[5] = ez;
 
   // upper bounds of the E loops are ub + Nb - 1 == M - 2 in the staggered directions
   const bool okx = idx.ix <= g.M[2] - 2;
   const bool oky = Dim >= 2 ? idx.iy <= g.M[1] - 2 : true;
   const bool okz = Dim >= 3 ? idx.iz <= g.M[0] - 2 : true;
 
-  const double bx = uf[c * 6 + 3], by = uf[c * 6 + 4], bz = uf[c * 6 + 5];
+  const double bx = ufc[3], by = ufc[4], bz = ufc[5];
+  // the reads of the neighbours' B precede the barrier below; E (written here) is nobody's input
 
   if (Dim == 1) {
-    uf[c * 6 + 0] = ex + (-delt * uj[c * 4 + 1]);
+    ufc[0] = ex + (-delt * ujc[1]);
     if (okx) {
-      uf[c * 6 + 1] = ey + ((-cflx) * (uf[(c + sx) * 6 + 5] - bz) - delt * uj[c * 4 + 2]);
-      uf[c * 6 + 2] = ez + ((+cflx) * (uf[(c + sx) * 6 + 4] - by) - delt * uj[c * 4 + 3]);
+      ufc[1] = ey + ((-cflx) * (ufx[5] - bz) - delt * ujc[2]);
+      ufc[2] = ez + ((+cflx) * (ufx[4] - by) - delt * ujc[3]);
     }
   } else if (Dim == 2) {
     if (oky) {
-      uf[c * 6 + 0] = ex + ((+cfly) * (uf[(c + sy) * 6 + 5] - bz) - delt * uj[c * 4 + 1]);
+      ufc[0] = ex + ((+cfly) * (ufy[5] - bz) - delt * ujc[1]);
     }
     if (okx) {
-      uf[c * 6 + 1] = ey + ((-cflx) * (uf[(c + sx) * 6 + 5] - bz) - delt * uj[c * 4 + 2]);
+      ufc[1] = ey + ((-cflx) * (ufx[5] - bz) - delt * ujc[2]);
     }
     if (okx && oky) {
-      uf[c * 6 + 2] = ez + ((+cflx) * (uf[(c + sx) * 6 + 4] - by) +
-                            (-cfly) * (uf[(c + sy) * 6 + 3] - bx) - delt * uj[c * 4 + 3]);
+      ufc[2] = ez + ((+cflx) * (ufx[4] - by) + (-cfly) * (ufy[3] - bx) - delt * ujc[3]);
     }
   } else {
     if (okz && oky) {
-      uf[c * 6 + 0] = ex + ((+cfly) * (uf[(c + sy) * 6 + 5] - bz) +
-                            (-cflz) * (uf[(c + sz) * 6 + 4] - by) - delt * uj[c * 4 + 1]);
+      ufc[0] = ex + ((+cfly) * (ufy[5] - bz) + (-cflz) * (ufz[4] - by) - delt * ujc[1]);
     }
     if (okz && okx) {
-      uf[c * 6 + 1] = ey + ((+cflz) * (uf[(c + sz) * 6 + 3] - bx) +
-                            (-cflx) * (uf[(c + sx) * 6 + 5] - bz) - delt * uj[c * 4 + 2]);
+      ufc[1] = ey + ((+cflz) * (ufz[3] - bx) + (-cflx) * (ufx[5] - bz) - delt * ujc[2]);
     }
     if (oky && okx) {
-      uf[c * 6 + 2] = ez + ((+cflx) * (uf[(c + sx) * 6 + 4] - by) +
-                            (-cfly) * (uf[(c + sy) * 6 + 3] - bx) - delt * uj[c * 4 + 3]);
+      ufc[2] = ez + ((+cflx) * (ufx[4] - by) + (-cfly) * (ufy[3] - bx) - delt * ujc[3]);
     }
+  }
+  if (first >= 0) {
+    __syncthreads();
+    stage_out<6>(d.uf, s_uf, first);
+    stage_out<9>(d.ff, s_ff, first);
   }
 }
 

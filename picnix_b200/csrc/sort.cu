@@ -119,32 +119,46 @@ scatter_kernel(Geom g, DevPtrs d, int seg0, int blocks_per_seg)
     d.xv[k * d.pcap + off + dst] = d.xu[k * d.pcap + off + ip];
 }
 
-// lazy sort: same cursor logic, but only the permutation is written
+// lazy sort: same cursor logic, but only the permutation is written.  The kernel is a chain of dependent
+// round trips (key load -> match -> L2 atomic -> store), so every warp keeps INDEX_ILP independent chains
+// in flight: it owns INDEX_ILP * 32 consecutive particles, lane-contiguous per chain.
+constexpr int INDEX_ILP = 4;
+
 __global__ void __launch_bounds__(SCATTER_THREADS)
 scatter_index_kernel(Geom g, DevPtrs d, int seg0, int blocks_per_seg)
 {
   const int lseg = blockIdx.x / blocks_per_seg;
   const int b    = blockIdx.x - lseg * blocks_per_seg;
   const int seg  = seg0 + lseg;
-  const int ip   = b * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int n    = min(d.np[seg] + d.ntail[seg], d.seg_cap[seg]);
-  if (b * (int)blockDim.x + (int)(threadIdx.x & ~31u) >= n)
+  // first particle of this warp
+  const int w0   = (b * (SCATTER_THREADS / 32) + (threadIdx.x >> 5)) * (32 * INDEX_ILP);
+  if (w0 >= n)
     return;
 
-  const int64_t off  = d.seg_off[seg];
-  const int     key  = ip < n ? d.gindex[off + ip] : g.Ng;
-  const bool    keep = key < g.Ng;
-
-  const unsigned peers  = __match_any_sync(0xffffffffu, key);
-  const int      leader = __ffs(peers) - 1;
-  int            base   = 0;
-  if (keep && lane == leader)
-    base = atomicAdd(d.pcount + (int64_t)seg * (g.Ng + 1) + key, __popc(peers));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (!keep)
-    return;
-  d.perm[off + base + __popc(peers & ((1u << lane) - 1u))] = ip;
+  const int64_t off = d.seg_off[seg];
+  int*          cur = d.pcount + (int64_t)seg * (g.Ng + 1);
+  int           key[INDEX_ILP], base[INDEX_ILP];
+  unsigned      peers[INDEX_ILP];
+#pragma unroll
+  for (int j = 0; j < INDEX_ILP; j++) {
+    const int ip = w0 + j * 32 + lane;
+    key[j]       = ip < n ? d.gindex[off + ip] : g.Ng;
+  }
+#pragma unroll
+  for (int j = 0; j < INDEX_ILP; j++) {
+    peers[j] = __match_any_sync(0xffffffffu, key[j]);
+    base[j]  = 0;
+    if (key[j] < g.Ng && lane == __ffs(peers[j]) - 1)
+      base[j] = atomicAdd(cur + key[j], __popc(peers[j]));
+  }
+#pragma unroll
+  for (int j = 0; j < INDEX_ILP; j++) {
+    base[j] = __shfl_sync(0xffffffffu, base[j], __ffs(peers[j]) - 1);
+    if (key[j] < g.Ng)
+      d.perm[off + base[j] + __popc(peers[j] & ((1u << lane) - 1u))] = w0 + j * 32 + lane;
+  }
 }
 
 // materialise a pending lazy sort: xv[sorted slot] <- xu[perm[sorted slot]]
@@ -208,8 +222,10 @@ int launch_sort(picnix_arena* a, int c0, int cn)
   // the tiled push kernel reads through the permutation: no need to move the particles now
   const bool lazy = a->lazy_sort && !a->force_generic && row_geometry_applies(a);
   if (bps > 0) {
-    if (lazy)
-      scatter_index_kernel<<<bps * nseg, SCATTER_THREADS, 0, a->stream>>>(g, a->d, seg0, bps);
+    if (lazy) {
+      const int bpi = (maxcap + SCATTER_THREADS * INDEX_ILP - 1) / (SCATTER_THREADS * INDEX_ILP);
+      scatter_index_kernel<<<bpi * nseg, SCATTER_THREADS, 0, a->stream>>>(g, a->d, seg0, bpi);
+    }
     else
       scatter_kernel<<<bps * nseg, SCATTER_THREADS, 0, a->stream>>>(g, a->d, seg0, bps);
     a->kernel_launches++;
