@@ -10,10 +10,9 @@
 //       t += ww, (x,y,z) += ww u/gamma, (tx,ty,tz) += ww u, tt += ww gamma c, pairs += ww u_i u_j / gamma
 //
 // Diagnostics cadence, not the per-step hot path.  Two kernels:
-//   * moment_cell_kernel  -- cell-ordered particles, even orders with (Order+1)^Dim <= 32 (the
-//     BASELINE configurations): one warp per (segment, cell); lane = stencil point; the warp walks the
-//     cell's particles (uniform loads), every lane keeps its 14 sums in registers and the cell
-//     costs 14 reductions per stencil point instead of 14 per particle and point.
+//   * moment_row_kernel   -- cell-ordered particles, even orders with (Order+1)^Dim <= 32 (the
+//     BASELINE configurations): a warp per run of cells, per-particle factors staged once in shared
+//     memory, lane = stencil point for the accumulation, a private shared tile per run (see below).
 //   * moment_generic_kernel -- anything else: thread per particle, fp64 reductions to global.
 // Results differ from the reference by summation order only (tests: 1e-12 of max |um|).
 #include "particle_common.cuh"
@@ -105,33 +104,60 @@ moment_generic_kernel(Geom g, DevPtrs d, int blocks_per_seg)
       }
 }
 
-__device__ __forceinline__ double pick(const double* w, int j, int n)
-{
-  double r = w[0];
-#pragma unroll
-  for (int k = 1; k < 5; k++)
-    if (k < n && j == k)
-      r = w[k];
-  return r;
-}
+// ------------------------------------------------------------------------------------------------
+// Row-tile kernel (cell-ordered particles, even orders with (Order+1)^Dim <= 32: the BASELINE
+// configurations).  One warp owns a run of MRUN cells of one row and one species:
+//   phase A  lane = particle (coalesced loads, next batch prefetched into registers): gamma, the N weights
+//            per axis and the 14 per-particle factors go to a shared record -- formed once per particle;
+//   phase B  lane = stencil point: ww = wx[px] wy[py] wz[pz] and 14 FMAs per particle into registers
+//            (the record is read with warp-uniform loads);
+//   per cell the 14 sums of every point are added to the warp's shared tile (plain adds, the tile is
+//   private), and the tile goes to `um` once per run with one reduction per tile element: about
+//   (MRUN + N - 1) / MRUN * N^(Dim-1) * 14 global reductions per cell instead of N^Dim * 14.
+// ------------------------------------------------------------------------------------------------
+constexpr int MRUN   = 8;
+constexpr int MWARPS = MTHREADS / 32;
+constexpr int MPS    = NMOM + 1; // tile stride of a point: odd number of doubles (no bank conflicts)
 
-// one warp per (segment, sort key); lane = stencil point
+template <int Dim, int Order>
+struct MomentTile {
+  static constexpr int N    = Order + 1;
+  static constexpr int NY   = Dim >= 2 ? N : 1;
+  static constexpr int NZ   = Dim >= 3 ? N : 1;
+  static constexpr int NPTS = N * NY * NZ;
+  static constexpr int XT   = MRUN + N - 1;
+  static constexpr int TILE = XT * NY * NZ * MPS;
+  static constexpr int REC  = 3 * N + NMOM + ((3 * N + NMOM) % 2 == 0 ? 1 : 0); // odd record stride
+  static constexpr size_t BYTES = sizeof(double) * MWARPS * (TILE + 32 * REC);
+};
+
 template <int Dim, int Order>
 __global__ void __launch_bounds__(MTHREADS)
-moment_cell_kernel(Geom g, DevPtrs d)
+moment_row_kernel(Geom g, DevPtrs d)
 {
-  constexpr int N    = Order + 1;
-  constexpr int NPTS = Dim == 3 ? N * N * N : (Dim == 2 ? N * N : N);
-  const int64_t w    = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int     lane = threadIdx.x & 31;
-  const int     seg  = (int)(w / g.Ng);
-  const int     key  = (int)(w - (int64_t)seg * g.Ng);
-  if (seg >= g.nchunk * g.Ns)
+  using T = MomentTile<Dim, Order>;
+  constexpr int N = T::N, NY = T::NY, NZ = T::NZ, NPTS = T::NPTS, XT = T::XT, TILE = T::TILE, REC = T::REC;
+  extern __shared__ double msm[];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double*   tile = msm + warp * (TILE + 32 * REC);
+  double*   rec  = tile + TILE;
+
+  // warp -> (segment, z, y, run of MRUN cells in x)
+  const int     nrun = (g.dims[2] + MRUN - 1) / MRUN;
+  const int     ny   = Dim >= 2 ? g.dims[1] : 1;
+  const int     nz   = Dim >= 3 ? g.dims[0] : 1;
+  const int64_t w    = (int64_t)blockIdx.x * MWARPS + warp;
+  const int64_t per_seg = (int64_t)nz * ny * nrun;
+  if (w >= per_seg * g.nchunk * g.Ns)
     return;
-  const int* pix = d.pindex + (int64_t)seg * (g.Ng + 1);
-  const int  pb = pix[key], pe = pix[key + 1];
-  if (pe <= pb)
-    return;
+  const int seg = (int)(w / per_seg);
+  int       r   = (int)(w - (int64_t)seg * per_seg);
+  const int jz  = r / (ny * nrun);
+  r -= jz * ny * nrun;
+  const int jy  = r / nrun;
+  const int x0  = (r - jy * nrun) * MRUN;
+  const int len = min(MRUN, g.dims[2] - x0);
 
   const int     chunk = seg / g.Ns, is = seg - chunk * g.Ns;
   const int64_t off = d.seg_off[seg];
@@ -139,48 +165,116 @@ moment_cell_kernel(Geom g, DevPtrs d)
   const double  ms  = d.qm[2 * is + 1];
   const double  rc  = 1 / g.cc;
 
-  // cell of this key (XtensorParticle::flatindex, nix/xtensor_particle.hpp:231-238); even order:
-  // every particle of the cell has the same stencil origin
-  const int jz = key / g.fsz, jy = (key - jz * g.fsz) / g.fsy, jx = key - jz * g.fsz - jy * g.fsy;
-  const int px = lane % N, py = Dim >= 2 ? (lane / N) % N : 0, pz = Dim >= 3 ? lane / (N * N) : 0;
+  // particles of the run: [pix[key0], pix[key0 + len]) with the cell boundaries in between
+  const int* pix  = d.pindex + (int64_t)seg * (g.Ng + 1) + (Dim >= 3 ? jz * g.fsz : 0) + (Dim >= 2 ? jy * g.fsy : 0) + x0;
+  const int  pcut = lane <= len ? pix[lane] : 0;
+  const int  pbeg = __shfl_sync(0xffffffffu, pcut, 0), pend = __shfl_sync(0xffffffffu, pcut, len);
+  if (pend <= pbeg)
+    return;
 
-  double acc[NMOM];
+  for (int e = lane; e < TILE; e += 32)
+    tile[e] = 0;
+
+  const int px = lane % N, py = Dim >= 2 ? (lane / N) % N : 0, pz = Dim >= 3 ? lane / (N * N) : 0;
+  double    acc[NMOM];
 #pragma unroll
   for (int k = 0; k < NMOM; k++)
     acc[k] = 0;
 
-  for (int ip = pb; ip < pe; ip++) {
-    const int64_t i  = off + ip;
-    const double  ux = d.xu[3 * d.pcap + i], uy = d.xu[4 * d.pcap + i], uz = d.xu[5 * d.pcap + i];
-    const double  gm = sqrt(1 + (ux * ux + uy * uy + uz * uz) * rc * rc);
-    const double  rg = 1 / gm;
-    double        wx[N], wy[N], wz[N];
-    moment_axis<Order>(d.xu[0 * d.pcap + i], lim[4], g.del[2], g.Lb[2], wx);
-    double ww = ms * pick(wx, px, N);
-    if (Dim >= 2) {
-      moment_axis<Order>(d.xu[1 * d.pcap + i], lim[2], g.del[1], g.Lb[1], wy);
-      ww = ww * pick(wy, py, N);
-    }
-    if (Dim >= 3) {
-      moment_axis<Order>(d.xu[2 * d.pcap + i], lim[0], g.del[0], g.Lb[0], wz);
-      ww = ww * pick(wz, pz, N);
-    }
-    double t[NMOM];
-    moment_terms(ww, ux, uy, uz, gm, rg, g.cc, t);
+  // the stream of batches: at most 32 particles, never across a cell boundary
+  int    c = 0, base = pbeg; // current cell of the run and first particle of the current batch
+  double nx[6];
+  auto   fetch = [&](int cell, int b0) {
+    const int pe = __shfl_sync(0xffffffffu, pcut, cell + 1);
+    if (b0 + lane < pe) {
+      const int64_t i = off + b0 + lane;
 #pragma unroll
-    for (int k = 0; k < NMOM; k++)
-      acc[k] += t[k];
+      for (int k = 0; k < 6; k++)
+        nx[k] = d.xu[k * d.pcap + i];
+    }
+  };
+  while (c < len && __shfl_sync(0xffffffffu, pcut, c + 1) <= base)
+    c++; // leading empty cells
+  fetch(c, base);
+
+  while (base < pend) {
+    const int pe = __shfl_sync(0xffffffffu, pcut, c + 1);
+    const int n  = min(32, pe - base);
+    // ---- phase A: one particle per lane ----
+    if (lane < n) {
+      const double ux = nx[3], uy = nx[4], uz = nx[5];
+      const double gm = sqrt(1 + (ux * ux + uy * uy + uz * uz) * rc * rc);
+      const double rg = 1 / gm;
+      double*      q  = rec + lane * REC;
+      double       wgt[N];
+      moment_axis<Order>(nx[0], lim[4], g.del[2], g.Lb[2], wgt);
+#pragma unroll
+      for (int k = 0; k < N; k++)
+        q[k] = ms * wgt[k];
+      if (Dim >= 2) {
+        moment_axis<Order>(nx[1], lim[2], g.del[1], g.Lb[1], wgt);
+#pragma unroll
+        for (int k = 0; k < N; k++)
+          q[N + k] = wgt[k];
+      }
+      if (Dim >= 3) {
+        moment_axis<Order>(nx[2], lim[0], g.del[0], g.Lb[0], wgt);
+#pragma unroll
+        for (int k = 0; k < N; k++)
+          q[2 * N + k] = wgt[k];
+      }
+      moment_terms(1.0, ux, uy, uz, gm, rg, g.cc, q + 3 * N);
+    }
+    // next batch: same cell, or the next non-empty one
+    int nc = c, nbase = base + n;
+    while (nc < len && __shfl_sync(0xffffffffu, pcut, nc + 1) <= nbase)
+      nc++;
+    if (nbase < pend)
+      fetch(nc, nbase);
+    __syncwarp();
+    // ---- phase B: one stencil point per lane ----
+    if (lane < NPTS) {
+      for (int p = 0; p < n; p++) {
+        const double* q  = rec + p * REC;
+        double        ww = q[px];
+        if (Dim >= 2)
+          ww = ww * q[N + py];
+        if (Dim >= 3)
+          ww = ww * q[2 * N + pz];
+#pragma unroll
+        for (int k = 0; k < NMOM; k++)
+          acc[k] += ww * q[3 * N + k];
+      }
+    }
+    __syncwarp();
+    if (nc != c || nbase >= pend) {
+      // the cell is complete: its sums go to the tile
+      if (lane < NPTS) {
+        double* t = tile + (((c + px) * NY + py) * NZ + pz) * MPS;
+#pragma unroll
+        for (int k = 0; k < NMOM; k++) {
+          t[k] += acc[k];
+          acc[k] = 0;
+        }
+      }
+      __syncwarp();
+    }
+    c    = nc;
+    base = nbase;
   }
 
-  if (lane < NPTS) {
-    const int ix = jx + g.Lb[2] - Order / 2 + px;
-    const int iy = Dim >= 2 ? jy + g.Lb[1] - Order / 2 + py : g.Lb[1];
-    const int iz = Dim >= 3 ? jz + g.Lb[0] - Order / 2 + pz : g.Lb[0];
-    double*   m  = d.um + (int64_t)chunk * g.Ng * g.Ns * NMOM +
-                ((((int64_t)iz * g.M[1] + iy) * g.M[2] + ix) * g.Ns + is) * NMOM;
-#pragma unroll
-    for (int k = 0; k < NMOM; k++)
-      atomicAdd(m + k, acc[k]);
+  // tile -> um; first point of the run's first cell: (jz, jy, x0) + lb - Order/2
+  double*   um  = d.um + (int64_t)chunk * g.Ng * g.Ns * NMOM;
+  const int ix0 = x0 + g.Lb[2] - Order / 2;
+  const int iy0 = Dim >= 2 ? jy + g.Lb[1] - Order / 2 : g.Lb[1];
+  const int iz0 = Dim >= 3 ? jz + g.Lb[0] - Order / 2 : g.Lb[0];
+  for (int e = lane; e < XT * NY * NZ * NMOM; e += 32) {
+    const int    pt = e / NMOM, k = e - pt * NMOM;
+    const double v  = tile[pt * MPS + k];
+    if (v != 0.0) {
+      const int tx = pt / (NY * NZ), ty = (pt / NZ) % NY, tz = pt % NZ;
+      atomicAdd(um + ((((int64_t)(iz0 + tz) * g.M[1] + iy0 + ty) * g.M[2] + ix0 + tx) * g.Ns + is) * NMOM + k, v);
+    }
   }
 }
 
@@ -269,9 +363,12 @@ void launch_moment_kernels(picnix_arena* a)
   constexpr int N    = Order + 1;
   constexpr int NPTS = Dim == 3 ? N * N * N : (Dim == 2 ? N * N : N);
   if (a->pindex_valid && Order % 2 == 0 && NPTS <= 32 && !a->force_generic) {
-    const int64_t warps  = (int64_t)a->nseg * g.Ng;
-    const int64_t blocks = (warps * 32 + MTHREADS - 1) / MTHREADS;
-    moment_cell_kernel<Dim, Order><<<(unsigned)blocks, MTHREADS, 0, a->stream>>>(g, a->d);
+    using T = MomentTile<Dim, Order>;
+    auto          kern  = moment_row_kernel<Dim, Order>;
+    const int     nrun  = (g.dims[2] + MRUN - 1) / MRUN;
+    const int64_t warps = (int64_t)a->nseg * (Dim >= 3 ? g.dims[0] : 1) * (Dim >= 2 ? g.dims[1] : 1) * nrun;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::BYTES);
+    kern<<<(unsigned)((warps + MWARPS - 1) / MWARPS), MTHREADS, T::BYTES, a->stream>>>(g, a->d);
   } else {
     int maxcap = 0;
     for (int s = 0; s < a->nseg; s++)

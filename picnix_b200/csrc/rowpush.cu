@@ -9,6 +9,9 @@
 // particles of a row segment are contiguous in every species' cell-sorted arrays,
 // [pindex[key0], pindex[key0+RX]); the warp walks them as ONE stream, cell by cell, all species of a cell
 // back to back, every cell starting at an even stream slot.
+#ifndef PICNIX_INTERP_ANCHORED
+#define PICNIX_INTERP_ANCHORED 1
+#endif
 #include "rowtile.cuh"
 
 namespace picnix
@@ -315,7 +318,7 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
         // weights on the centre grid (MC or WT) and on the edge grid (MC); the particle is in cell
         // (jz, jy, cx) by construction of the sort
         double s0x[3], s0y[3], s0z[3];
-        double wix[3], wiy[3], wiz[3], h[3], whx[4], why[4], whz[4];
+        double wix[3], wiy[3], wiz[3], h[3];
         const double dix = (x0 - (xigrid + cxf * dx)) * rdx;
         const double diy = (y0 - yig) * rdy;
         const double diz = (z0 - zig) * rdz;
@@ -334,9 +337,14 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
           shape_wt<2>(y0, yig, rdy, rc.cfl[1], 1 / rc.cfl[1], wiy);
           shape_wt<2>(z0, zig, rdz, rc.cfl[0], 1 / rc.cfl[0], wiz);
         }
-        // nearest cell edge: the one to the right when the particle sits right of the centre; its
-        // three weights go into the cell-anchored 4-slot array
+        // nearest cell edge: the one to the right when the particle sits right of the centre
         const bool hx = dix >= 0.0, hy = diy >= 0.0, hz = diz >= 0.0;
+        const double* F    = ftile + warp * FROW + jx * 6;
+        const double  qmdt = bs->qmdt[is];
+#if PICNIX_INTERP_ANCHORED
+        // cell-anchored 4-slot edge weights (one of the four is zero): every lane of a cell reads the
+        // same addresses, at the price of 4 instead of 3 points per staggered axis
+        double whx[4], why[4], whz[4];
         shape2((x0 - (xmin + (cxf + (hx ? 1.0 : 0.0)) * dx)) * rdx, h);
         shift4(h, hx, whx);
         shape2((y0 - (hy ? yh1 : yh0)) * rdy, h);
@@ -345,14 +353,30 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
         shift4(h, hz, whz);
 
         // first stencil point of the cell in the tile; Yee staggering, pic/engine/velocity.hpp:442-447
-        const double* F    = ftile + warp * FROW + jx * 6;
-        const double  qmdt = bs->qmdt[is];
         double ex = interp_cell<3, 3, 4>(F + 0, wiz, wiy, whx) * qmdt;
         double ey = interp_cell<3, 4, 3>(F + 1, wiz, why, wix) * qmdt;
         double ez = interp_cell<4, 3, 3>(F + 2, whz, wiy, wix) * qmdt;
         double bx = interp_cell<4, 4, 3>(F + 3, whz, why, wix) * qmdt;
         double by = interp_cell<4, 3, 4>(F + 4, whz, wiy, whx) * qmdt;
         double bz = interp_cell<3, 4, 4>(F + 5, wiz, why, whx) * qmdt;
+#else
+        // three points per axis; on the staggered axes the stencil starts one slot further right for
+        // the particles right of the centre (a per-lane tile offset: the loads of a cell are no longer
+        // uniform, but a third of the 4-slot form's loads and FMAs multiplied zeros)
+        double whx[3], why[3], whz[3];
+        shape2((x0 - (xmin + (cxf + (hx ? 1.0 : 0.0)) * dx)) * rdx, whx);
+        shape2((y0 - (hy ? yh1 : yh0)) * rdy, why);
+        shape2((z0 - (hz ? zh1 : zh0)) * rdz, whz);
+        const int ox = hx ? 6 : 0, oy = hy ? FROW : 0, oz = hz ? FSLAB : 0;
+
+        // Yee staggering, pic/engine/velocity.hpp:442-447
+        double ex = interp_cell<3, 3, 3>(F + 0 + ox, wiz, wiy, whx) * qmdt;
+        double ey = interp_cell<3, 3, 3>(F + 1 + oy, wiz, why, wix) * qmdt;
+        double ez = interp_cell<3, 3, 3>(F + 2 + oz, whz, wiy, wix) * qmdt;
+        double bx = interp_cell<3, 3, 3>(F + 3 + oy + oz, whz, why, wix) * qmdt;
+        double by = interp_cell<3, 3, 3>(F + 4 + ox + oz, whz, wiy, whx) * qmdt;
+        double bz = interp_cell<3, 3, 3>(F + 5 + ox + oy, wiz, why, whx) * qmdt;
+#endif
 
         if (Pusher == PICNIX_PUSHER_BORIS)
           push_boris_fast(ux, uy, uz, ex, ey, ez, bx, by, bz, rc.cc);
