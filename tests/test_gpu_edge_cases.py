@@ -140,6 +140,49 @@ def test_tiled_2d_kernel_variants_relativistic_multistep(pusher, interp):
     assert same and dx < 1e-11 and du < 1e-10
 
 
+def test_tiled_1d_kernel_far_movers_and_phases():
+    """The 1-D tiled kernel (rowpush1d.cu): one fused push + deposit against the reference's separate
+    calls with a time step so large that many particles cross more than one cell; then the deposit-only
+    path through the separate phases.  8-cell chunks: every chunk is one segment, a block spans four."""
+    for cdims in ((1, 1, 6), (1, 1, 3)):   # 8- and 16-cell chunks; 6 segments: the last block is ragged
+        ref, gpu = make_pair((1, 1, 48), cdims, problems.TWOSTREAM_SPECIES, (16, 16, 32), 50.0, B0=(10.0, 0, 0))
+        dt = 0.15   # the beams (u = 10) move 1.5 cells per step
+        ref.push_velocity(dt)
+        ref.push_position(dt)
+        ref.deposit_current(dt)
+        gpu.push_deposit_fused(dt)
+        dx, du, same = particle_err(gpu, ref, scale_x=48.0, scale_u=50.0)
+        assert same and dx < 1e-14 and du < 1e-13
+        assert keys_equal(gpu, ref)
+        assert field_err(gpu, ref, FIELD_UJ) < 1e-12
+        ref, gpu = make_pair((1, 1, 48), cdims, problems.TWOSTREAM_SPECIES, (16, 16, 32), 50.0, B0=(10.0, 0, 0))
+        for sim in (ref, gpu):
+            sim.push_velocity(dt)
+            sim.push_position(dt)
+            sim.deposit_current(dt)
+        assert field_err(gpu, ref, FIELD_UJ) < 1e-12
+
+
+@pytest.mark.parametrize("pusher,interp", [(0, 0), (0, 1), (1, 0), (2, 1)])
+def test_tiled_1d_kernel_variants_relativistic_multistep(pusher, interp):
+    """Pushers and WT interpolation through the tiled 1-D kernel at a relativistic temperature, four
+    species (the merged stream's maximum), ragged and empty segments, several steps."""
+    species = [dict(qm=-1.0, ro=1.0, vt=1.0), dict(qm=+0.1, ro=10.0, vt=0.3), dict(qm=-0.5, ro=0.5, vt=0.6),
+               dict(qm=+0.3, ro=2.0, vt=0.2, drift=(0.5, 0.1, -0.2))]
+    thin = lambda ic, isp, n: 0 if (ic == 2 and isp == 1) else (n if (ic + isp) % 3 else n // 3)
+    ref, gpu = make_pair((1, 1, 80), (1, 1, 5), species, (8, 5, 3, 6), 1.0, pusher=pusher, interp=interp,
+                         B0=(0.5, 0.2, 0.3), thin=thin)
+    dt = 0.4
+    ref.step(dt, 10)
+    gpu.step(dt, 10)
+    gpu.synchronize()
+    assert counts_equal(gpu, ref)
+    assert field_err(gpu, ref, FIELD_UF) < 1e-10
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-10
+    dx, du, same = particle_err(gpu, ref, scale_x=80.0, scale_u=1.0)
+    assert same and dx < 1e-11 and du < 1e-10
+
+
 def make_cherenkov_pair(ndims, cdims, nppc=16, u0=0.1, vt=0.1, delh=0.1, cc=1.0, order=2, seed=9):
     """example/cherenkov (main.cpp:31-160, config.toml): pair plasma (mime = 1) drifting with u0 along
     x, cell size delh = 0.1 (NOT 1), cc = 1, wp = 1: me = 1/nppc, qe = -wp/nppc*sqrt(gamma)."""
