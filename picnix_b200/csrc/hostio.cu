@@ -37,6 +37,9 @@ struct HostIO {
   bool                 used[NSLOT] = {false, false, false};
   bool                 ready       = false;
   std::vector<void*>   registered; // buffers this library page-locked
+  int64_t*             d_capoff    = nullptr; // prefix sums of the host capacities (grouped transfers)
+  int64_t*             h_capoff    = nullptr; // pinned staging of the same
+  int                  capoff_len  = 0;
 };
 
 void hostio_destroy(picnix_arena* a)
@@ -55,6 +58,10 @@ void hostio_destroy(picnix_arena* a)
       cudaEventDestroy(io->drained[s]);
     }
   }
+  if (io->d_capoff)
+    cudaFree(io->d_capoff);
+  if (io->h_capoff)
+    cudaFreeHost(io->h_capoff);
   if (io->ev_misc)
     cudaEventDestroy(io->ev_misc);
   if (io->h2d)
@@ -123,7 +130,49 @@ struct Piece {
   int64_t slab_off;
   int     id; // segment (particles) or first chunk (ff)
   int     n;  // particles / chunks
+  int     group = 0; // > 0: `id` is the first of `group` consecutive segments copied as one host span
+  int     maxn  = 0; // largest particle count in the group
 };
+
+// Arenas with very many segments (1-D runs) move their particles in groups of consecutive segments:
+// one copy of the host span (capacity gaps included) and one transposition launch per group instead of
+// one of each per segment (two-stream, 98 304 segments: 1.6 s -> tens of ms per step).
+constexpr int     GROUP_MIN_SEGMENTS = 2048;
+constexpr int     GROUP_MAX_SEGMENTS = 32768;      // blockIdx.y
+constexpr int64_t GROUP_MAX_ELEMS    = 8 << 20;    // 64 MB per copy keeps the three streams busy
+
+// particle pieces of the arena: per segment, or per group of segments
+static void particle_pieces(picnix_arena* a, HostIO* io, double* xu, const int32_t* np, const int32_t* np_cap,
+                            std::vector<Piece>& pieces)
+{
+  if (a->nseg < GROUP_MIN_SEGMENTS) {
+    int64_t poff = 0;
+    for (int s = 0; s < a->nseg; s++) {
+      pieces.push_back({xu + poff * NC, (int64_t)np[s] * NC, 0, s, np[s]});
+      poff += np_cap[s];
+    }
+    return;
+  }
+  const int64_t limit = std::min<int64_t>(io->slab_elems, GROUP_MAX_ELEMS);
+  int           s0    = 0;
+  while (s0 < a->nseg) {
+    int     s1 = s0, maxn = np[s0];
+    int64_t span = (int64_t)np[s0] * NC;
+    while (s1 + 1 < a->nseg && s1 + 1 - s0 < GROUP_MAX_SEGMENTS) {
+      const int64_t next = (io->h_capoff[s1 + 1] - io->h_capoff[s0] + np[s1 + 1]) * NC;
+      if (next > limit)
+        break;
+      s1++;
+      span = next;
+      maxn = std::max(maxn, np[s1]);
+    }
+    Piece p{xu + io->h_capoff[s0] * NC, span, 0, s0, 0};
+    p.group = s1 - s0 + 1;
+    p.maxn  = maxn;
+    pieces.push_back(p);
+    s0 = s1 + 1;
+  }
+}
 
 // split pieces into batches that fit a slab
 std::vector<std::vector<Piece>> make_batches(std::vector<Piece>& pieces, int64_t slab_elems)
@@ -172,6 +221,25 @@ static int hostio_prepare(picnix_arena* a, double* uf, double* uj, double* ff, d
   HostIO* io = nullptr;
   if ((status = hostio_get(a, max_seg, &io)) != PICNIX_OK)
     return status;
+  if (a->nseg >= GROUP_MIN_SEGMENTS) {
+    if (io->capoff_len < a->nseg + 1) {
+      if (io->d_capoff)
+        cudaFree(io->d_capoff);
+      if (io->h_capoff)
+        cudaFreeHost(io->h_capoff);
+      io->d_capoff = nullptr;
+      io->h_capoff = nullptr;
+      PICNIX_CUDA(a, cudaMalloc((void**)&io->d_capoff, (a->nseg + 1) * sizeof(int64_t)));
+      PICNIX_CUDA(a, cudaMallocHost((void**)&io->h_capoff, (a->nseg + 1) * sizeof(int64_t)));
+      io->capoff_len = a->nseg + 1;
+    }
+    io->h_capoff[0] = 0;
+    for (int s = 0; s < a->nseg; s++)
+      io->h_capoff[s + 1] = io->h_capoff[s] + np_cap[s];
+    // on the compute stream, which every transposition launch is ordered behind
+    PICNIX_CUDA(a, cudaMemcpyAsync(io->d_capoff, io->h_capoff, (a->nseg + 1) * sizeof(int64_t),
+                                   cudaMemcpyHostToDevice, a->stream));
+  }
   pin_if_needed(io, uf, (size_t)g.nchunk * ncell * 6 * sizeof(double));
   pin_if_needed(io, uj, (size_t)g.nchunk * ncell * 4 * sizeof(double));
   pin_if_needed(io, ff, (size_t)g.nchunk * ncell * 18 * sizeof(double));
@@ -216,11 +284,7 @@ int upload_state_pipelined(picnix_arena* a, double* uf, double* uj, double* ff, 
       pieces.push_back({ff + (int64_t)c * ncell * 18, (int64_t)n * ncell * 18, 0, -1 - c, n});
     }
   }
-  int64_t poff = 0;
-  for (int s = 0; s < a->nseg; s++) {
-    pieces.push_back({xu + poff * NC, (int64_t)np_in[s] * NC, 0, s, np_in[s]});
-    poff += np_cap[s];
-  }
+  particle_pieces(a, io, xu, np_in, np_cap, pieces);
   auto batches = make_batches(pieces, io->slab_elems);
 
   int slot = 0;
@@ -238,6 +302,13 @@ int upload_state_pipelined(picnix_arena* a, double* uf, double* uj, double* ff, 
         const int64_t nc = (int64_t)p.n * ncell;
         ff_compact_kernel<<<(unsigned)((nc * 9 + TTHREADS - 1) / TTHREADS), TTHREADS, 0, a->stream>>>(
             io->slab[slot] + p.slab_off, a->d.ff + (int64_t)c0 * ncell * 9, nc);
+      } else if (p.group > 0) {
+        if (p.maxn > 0) {
+          const dim3 grid((unsigned)(((int64_t)p.maxn * NC + TTHREADS - 1) / TTHREADS), (unsigned)p.group);
+          aos_to_soa_group_kernel<<<grid, TTHREADS, 0, a->stream>>>(io->slab[slot] + p.slab_off, a->d.xu,
+                                                                    io->d_capoff, a->d.seg_off, a->d.np, p.id,
+                                                                    a->d.pcap);
+        }
       } else {
         aos_to_soa_kernel<<<(unsigned)((p.elems + TTHREADS - 1) / TTHREADS), TTHREADS, 0, a->stream>>>(
             io->slab[slot] + p.slab_off, a->d.xu, a->seg_off[p.id], a->d.pcap, p.n);
@@ -288,11 +359,7 @@ int download_state_pipelined(picnix_arena* a, double* uf, double* uj, double* ff
                                  cudaMemcpyDeviceToHost, io->d2h));
 
   std::vector<Piece> pieces;
-  int64_t            poff = 0;
-  for (int s = 0; s < a->nseg; s++) {
-    pieces.push_back({xu + poff * NC, (int64_t)np_out[s] * NC, 0, s, np_out[s]});
-    poff += np_cap[s];
-  }
+  particle_pieces(a, io, xu, np_out, np_cap, pieces);
   {
     const int per = (int)std::max<int64_t>(1, io->slab_elems / (ncell * 18));
     for (int c = 0; c < g.nchunk; c += per) {
@@ -312,6 +379,13 @@ int download_state_pipelined(picnix_arena* a, double* uf, double* uj, double* ff
         const int64_t nc = (int64_t)p.n * ncell;
         ff_expand_kernel<<<(unsigned)((nc * 18 + TTHREADS - 1) / TTHREADS), TTHREADS, 0, a->stream>>>(
             a->d.ff + (int64_t)c0 * ncell * 9, io->slab[slot] + p.slab_off, nc);
+      } else if (p.group > 0) {
+        if (p.maxn > 0) {
+          const dim3 grid((unsigned)(((int64_t)p.maxn * NC + TTHREADS - 1) / TTHREADS), (unsigned)p.group);
+          soa_to_aos_group_kernel<<<grid, TTHREADS, 0, a->stream>>>(a->d.xu, io->slab[slot] + p.slab_off,
+                                                                    io->d_capoff, a->d.seg_off, a->d.np, p.id,
+                                                                    a->d.pcap);
+        }
       } else {
         soa_to_aos_kernel<<<(unsigned)((p.elems + TTHREADS - 1) / TTHREADS), TTHREADS, 0, a->stream>>>(
             a->d.xu, io->slab[slot] + p.slab_off, a->seg_off[p.id], a->d.pcap, p.n);

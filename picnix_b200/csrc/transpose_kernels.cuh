@@ -37,6 +37,37 @@ static __global__ void soa_to_aos_kernel(const double* __restrict__ soa, double*
   aos[i] = soa[ic * pcap + off + ip];
 }
 
+// Many small segments (1-D runs: tens of thousands of 512-particle segments): one launch for a GROUP of
+// consecutive segments whose host span was copied in one piece.  capoff = prefix sums of the host
+// capacities (the host array keeps its capacity gaps, so does the staged copy); blockIdx.y = segment.
+static __global__ void aos_to_soa_group_kernel(const double* __restrict__ span, double* __restrict__ soa,
+                                               const int64_t* __restrict__ capoff,
+                                               const int64_t* __restrict__ seg_off,
+                                               const int* __restrict__ np, int s0, int64_t pcap)
+{
+  const int     s = s0 + blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)np[s] * NC)
+    return;
+  const int ip = (int)(i / NC);
+  const int ic = (int)(i - (int64_t)ip * NC);
+  soa[ic * pcap + seg_off[s] + ip] = span[(capoff[s] - capoff[s0]) * NC + i];
+}
+
+static __global__ void soa_to_aos_group_kernel(const double* __restrict__ soa, double* __restrict__ span,
+                                               const int64_t* __restrict__ capoff,
+                                               const int64_t* __restrict__ seg_off,
+                                               const int* __restrict__ np, int s0, int64_t pcap)
+{
+  const int     s = s0 + blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)np[s] * NC)
+    return;
+  const int ip = (int)(i / NC);
+  const int ic = (int)(i - (int64_t)ip * NC);
+  span[(capoff[s] - capoff[s0]) * NC + i] = soa[ic * pcap + seg_off[s] + ip];
+}
+
 //
 // ff: host layout [cell][3][6] (reference) <-> device layout [cell][3][3]
 //

@@ -57,6 +57,36 @@ def test_step_host_multi_step_call_equals_resident():
             assert np.array_equal(gpu.get_pindex(ic, isp), res.get_pindex(ic, isp))
 
 
+def test_step_host_many_small_segments_grouped_transfers():
+    """Arenas with thousands of segments (1-D runs) move their particles in groups of consecutive segments
+    (one host-span copy + one transposition launch per group, hostio.cu): a two-stream box of 768 8-cell
+    chunks x 3 species = 2304 segments through picnix_cuda_step_host equals the resident step."""
+    from picnix_b200 import CudaSim, problems
+
+    nd, cd = (1, 1, 8 * 768), (1, 1, 768)
+    sims = []
+    for _ in range(2):
+        sim = CudaSim(nd, cd, Ns=3, cc=50.0, delh=1.0, order=2)
+        problems.setup_uniform_plasma(sim, nd, cd, problems.TWOSTREAM_SPECIES, (16, 16, 32), B0=(10.0, 0, 0), seed=3)
+        sims.append(sim)
+    gpu, res = sims
+    st = gpu.host_state(pinned=True)
+    for _ in range(4):
+        gpu.step_host(st, 0.01, 1)
+    res.step(0.01, 4)
+    res.synchronize()
+    for ic in range(0, gpu.nchunk, 37):
+        a, b = host_field(gpu, st, ic, FIELD_UF), res.get_field(ic, FIELD_UF)
+        assert np.max(np.abs(a - b)) <= 1e-11 * max(np.max(np.abs(b)), 1e-300)
+        for isp in range(gpu.Ns):
+            assert st["np"][ic * gpu.Ns + isp] == res.get_np(ic, isp)
+            pa = sorted_by_id(gpu.host_particles(st, gpu.Ns, ic, isp))
+            pb = sorted_by_id(res.get_particles(ic, isp))
+            assert np.array_equal(pa[:, 6].view(np.int64), pb[:, 6].view(np.int64))
+            assert np.max(np.abs(pa[:, :6] - pb[:, :6])) < 1e-9
+    assert np.array_equal(st["np"].reshape(-1, 3), res.get_np_all())
+
+
 def test_host_alloc_roundtrip():
     import ctypes as C
 
