@@ -290,21 +290,39 @@ class DistributedSim(CudaSim):
                                      self.cfg.buffer_ratio))
         for isp, (q, m) in self._species.items():
             new.set_species(isp, q, m)
-        for gid in range(old_boundary[-1]):
-            src, dst = _owner(old_boundary, gid), _owner(new_boundary, gid)
-            if src == self.rank:
+        # chunks that stay are handed over device to device; the ones that change owner travel in ONE
+        # group of sends and receives: the packed sizes of all chunks are agreed on first (one reduction,
+        # one host read), so no message needs a size handshake of its own
+        nchunk_all = old_boundary[-1]
+        moves = [(gid, _owner(old_boundary, gid), _owner(new_boundary, gid)) for gid in range(nchunk_all)]
+        sizes = torch.zeros(nchunk_all, dtype=torch.int64, device="cuda")
+        mine_sizes = {}
+        for gid, src, dst in moves:
+            if src == self.rank and dst != self.rank:
+                mine_sizes[gid] = self.chunk_pack_size(gid - old_boundary[src])
+        if mine_sizes:
+            idx = torch.tensor(list(mine_sizes.keys()), dtype=torch.int64, device="cuda")
+            sizes[idx] = torch.tensor(list(mine_sizes.values()), dtype=torch.int64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(sizes)
+        sizes = sizes.cpu().numpy()
+        ops, arrivals, keep = [], [], []
+        for gid, src, dst in moves:
+            if src == self.rank and dst == self.rank:
+                new.chunk_unpack(gid - new_boundary[dst], self.chunk_pack(gid - old_boundary[src]))
+            elif src == self.rank:
                 buf = self.chunk_pack(gid - old_boundary[src])
-                if dst == self.rank:
-                    new.chunk_unpack(gid - new_boundary[dst], buf)
-                else:
-                    dist.send(torch.tensor([buf.numel()], dtype=torch.int64, device="cuda"), dst)
-                    dist.send(buf, dst)
+                keep.append(buf)
+                ops.append(dist.P2POp(dist.isend, buf, dst))
             elif dst == self.rank:
-                n = torch.zeros(1, dtype=torch.int64, device="cuda")
-                dist.recv(n, src)
-                buf = torch.empty(int(n.item()), dtype=torch.uint8, device="cuda")
-                dist.recv(buf, src)
-                new.chunk_unpack(gid - new_boundary[dst], buf)
+                buf = torch.empty(int(sizes[gid]), dtype=torch.uint8, device="cuda")
+                arrivals.append((gid, buf))
+                ops.append(dist.P2POp(dist.irecv, buf, src))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for gid, buf in arrivals:
+            new.chunk_unpack(gid - new_boundary[self.rank], buf)
         new.sort_particle()
         return new
 

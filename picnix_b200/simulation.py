@@ -147,6 +147,12 @@ class CudaSim:
         self._capacity_set = True
 
     # -- chunk moves (rebalancing): the whole state of a local chunk as one device buffer --------
+    def chunk_pack_size(self, ic):
+        self.commit()
+        n = C.c_int64()
+        self._check(self.lib.picnix_cuda_chunk_pack_size(self.h, ic, C.byref(n)))
+        return n.value
+
     def chunk_pack(self, ic):
         import torch
 
