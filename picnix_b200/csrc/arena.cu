@@ -508,14 +508,25 @@ int picnix_cuda_arena_destroy(picnix_arena_t* a)
     for (int m = 0; m < 3; m++) {
       dev_free(p.d_send_off[m]);
       dev_free(p.d_recv_off[m]);
-      dev_free(p.d_send[m]);
-      dev_free(p.d_recv[m]);
+      if (m == 2) { // Emf / Cur buffers are slices of d_send_all / d_recv_all
+        dev_free(p.d_send[m]);
+        dev_free(p.d_recv[m]);
+      }
     }
     dev_free(p.d_psend);
     dev_free(p.d_precv);
-    dev_free(p.d_psend_count);
-    dev_free(p.d_rcount);
+    p.d_psend_count = nullptr; // slices of d_mig_counts
+    p.d_rcount      = nullptr;
   }
+  for (int m = 0; m < 2; m++) {
+    dev_free(a->d_send_all[m]);
+    dev_free(a->d_recv_all[m]);
+    dev_free(a->d_send_off_all[m]);
+    dev_free(a->d_recv_off_all[m]);
+  }
+  dev_free(a->d_mig_counts);
+  dev_free(a->d_send_desc_all);
+  dev_free(a->d_recv_desc_all);
   if (a->own_stream && a->stream)
     cudaStreamDestroy(a->stream);
   delete a;

@@ -166,6 +166,17 @@ struct picnix_arena {
   bool                   mig_async_step  = false; // the exchange in flight uses the lagged-count protocol
   int*                   h_mig      = nullptr;    // pinned [npeer][2]: sent / received counts of the last step
   int64_t*               h_bounds   = nullptr;    // pinned [npeer]: per-step send bounds (device caps)
+  // fixed-size modes (Emf, Cur): the buffers of all peers are carved from one allocation per mode and
+  // direction, and the messages of all peers are listed in one table, so that a phase is ONE pack or
+  // unpack launch whatever the number of peers
+  double*                d_send_all[2] = {nullptr, nullptr};
+  double*                d_recv_all[2] = {nullptr, nullptr};
+  int*                   d_send_desc_all = nullptr;
+  int*                   d_recv_desc_all = nullptr;
+  int64_t*               d_send_off_all[2] = {nullptr, nullptr};
+  int64_t*               d_recv_off_all[2] = {nullptr, nullptr};
+  int                    nmsg_send_all = 0, nmsg_recv_all = 0;
+  int*                   d_mig_counts  = nullptr; // [npeer][2]: records sent / found in the received header
   cudaEvent_t            mig_event  = nullptr;
   bool                   mig_pending = false;     // h_mig will hold the counts of the last step after mig_event
   bool                   perm_pending = false;  // xu is NOT yet in pindex order: DevPtrs::perm holds the order

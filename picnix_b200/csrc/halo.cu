@@ -434,7 +434,25 @@ int build_comm_plan(picnix_arena* a)
 
   // device side of the plan
   int status;
-  for (auto& p : a->peers) {
+  // one allocation per fixed-size mode and direction; a peer's buffer is a 16-byte aligned slice of it
+  std::vector<int64_t> sbase[2], rbase[2];
+  for (int mode = 0; mode < 2; mode++) {
+    int64_t stot = 0, rtot = 0;
+    for (auto& p : a->peers) {
+      sbase[mode].push_back(stot);
+      rbase[mode].push_back(rtot);
+      stot += (std::max<int64_t>(p.send_elems[mode], 1) + 1) & ~(int64_t)1;
+      rtot += (std::max<int64_t>(p.recv_elems[mode], 1) + 1) & ~(int64_t)1;
+    }
+    if (!a->peers.empty()) {
+      PICNIX_CUDA(a, cudaMalloc((void**)&a->d_send_all[mode], stot * sizeof(double)));
+      PICNIX_CUDA(a, cudaMalloc((void**)&a->d_recv_all[mode], rtot * sizeof(double)));
+    }
+  }
+  std::vector<int>     sdesc_all, rdesc_all;
+  std::vector<int64_t> soff_all[2], roff_all[2];
+  for (size_t ip = 0; ip < a->peers.size(); ip++) {
+    PeerPlan&        p = a->peers[ip];
     std::vector<int> sdesc, rdesc;
     for (size_t m = 0; m < p.send_chunk.size(); m++) {
       sdesc.push_back(p.send_chunk[m]);
@@ -444,6 +462,8 @@ int build_comm_plan(picnix_arena* a)
       rdesc.push_back(p.recv_chunk[m]);
       rdesc.push_back(p.recv_dir[m]);
     }
+    sdesc_all.insert(sdesc_all.end(), sdesc.begin(), sdesc.end());
+    rdesc_all.insert(rdesc_all.end(), rdesc.begin(), rdesc.end());
     if ((status = upload_vector(a, &p.d_send_desc, sdesc)) != PICNIX_OK)
       return status;
     if ((status = upload_vector(a, &p.d_recv_desc, rdesc)) != PICNIX_OK)
@@ -455,13 +475,34 @@ int build_comm_plan(picnix_arena* a)
         return status;
       if (mode == PICNIX_BOUNDARY_MOM)
         continue; // diagnostics cadence: buffers are allocated by the first moment exchange
-      PICNIX_CUDA(a, cudaMalloc((void**)&p.d_send[mode],
-                                std::max<int64_t>(p.send_elems[mode], 1) * sizeof(double)));
-      PICNIX_CUDA(a, cudaMalloc((void**)&p.d_recv[mode],
-                                std::max<int64_t>(p.recv_elems[mode], 1) * sizeof(double)));
+      p.d_send[mode] = a->d_send_all[mode] + sbase[mode][ip];
+      p.d_recv[mode] = a->d_recv_all[mode] + rbase[mode][ip];
+      for (int64_t o : p.send_msg_off[mode])
+        soff_all[mode].push_back(o + sbase[mode][ip]);
+      for (int64_t o : p.recv_msg_off[mode])
+        roff_all[mode].push_back(o + rbase[mode][ip]);
     }
-    PICNIX_CUDA(a, cudaMalloc((void**)&p.d_psend_count, 2 * sizeof(int)));
-    PICNIX_CUDA(a, cudaMemset(p.d_psend_count, 0, 2 * sizeof(int)));
+  }
+  // migration counters of all peers in one array: one clear and one copy to the host per step
+  if (!a->peers.empty()) {
+    PICNIX_CUDA(a, cudaMalloc((void**)&a->d_mig_counts, a->peers.size() * 2 * sizeof(int)));
+    PICNIX_CUDA(a, cudaMemset(a->d_mig_counts, 0, a->peers.size() * 2 * sizeof(int)));
+    for (size_t ip = 0; ip < a->peers.size(); ip++) {
+      a->peers[ip].d_psend_count = a->d_mig_counts + 2 * ip;
+      a->peers[ip].d_rcount      = a->d_mig_counts + 2 * ip + 1;
+    }
+  }
+  a->nmsg_send_all = (int)sdesc_all.size() / 2;
+  a->nmsg_recv_all = (int)rdesc_all.size() / 2;
+  if (a->nmsg_send_all > 0 && (status = upload_vector(a, &a->d_send_desc_all, sdesc_all)) != PICNIX_OK)
+    return status;
+  if (a->nmsg_recv_all > 0 && (status = upload_vector(a, &a->d_recv_desc_all, rdesc_all)) != PICNIX_OK)
+    return status;
+  for (int mode = 0; mode < 2; mode++) {
+    if (a->nmsg_send_all > 0 && (status = upload_vector(a, &a->d_send_off_all[mode], soff_all[mode])) != PICNIX_OK)
+      return status;
+    if (a->nmsg_recv_all > 0 && (status = upload_vector(a, &a->d_recv_off_all[mode], roff_all[mode])) != PICNIX_OK)
+      return status;
   }
   if (!a->slot_peer.empty()) {
     if ((status = upload_vector(a, &a->d_slot_peer, a->slot_peer)) != PICNIX_OK)
@@ -498,8 +539,6 @@ static int ensure_particle_staging(picnix_arena* a)
     // + 1 record: the lagged-count protocol appends a 64-byte header (the record count)
     PICNIX_CUDA(a, cudaMalloc((void**)&p.d_psend, (cap + 1) * 8 * sizeof(double)));
     PICNIX_CUDA(a, cudaMalloc((void**)&p.d_precv, (cap + 1) * 8 * sizeof(double)));
-    PICNIX_CUDA(a, cudaMalloc((void**)&p.d_rcount, sizeof(int)));
-    PICNIX_CUDA(a, cudaMemset(p.d_rcount, 0, sizeof(int)));
     ptrs.push_back(p.d_psend);
     cnts.push_back(p.d_psend_count);
     caps.push_back(cap);
@@ -533,14 +572,23 @@ __global__ void migration_header_kernel(double** psend, int** counts, const int6
     psend[i][bounds[i] * 8] = (double)*counts[i];
 }
 
+// the received messages of all peers in one launch: blockIdx.y = peer
+constexpr int MAX_PEERS = 32;
+struct PeerRecv {
+  const double* recv[MAX_PEERS];
+  int64_t       bound[MAX_PEERS];
+};
+
 __global__ void __launch_bounds__(HALO_THREADS)
-unpack_particle_bounded_kernel(Geom g, DevPtrs d, const double* __restrict__ recv, int64_t bound,
-                               int* rcount, int chunk_begin)
+unpack_particle_all_kernel(Geom g, DevPtrs d, PeerRecv pr, int* __restrict__ counts, int chunk_begin)
 {
-  const int count = (int)recv[bound * 8];
-  const int nrec  = count < bound ? count : (int)bound;
+  const int     peer  = blockIdx.y;
+  const double* recv  = pr.recv[peer];
+  const int64_t bound = pr.bound[peer];
+  const int     count = (int)recv[bound * 8];
+  const int     nrec  = count < bound ? count : (int)bound;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    *rcount = count;
+    counts[2 * peer + 1] = count;
     if (count > bound)
       atomicExch(d.errflag + 1, 1);
   }
@@ -667,14 +715,12 @@ int launch_halo_begin(picnix_arena* a, int mode)
 
   switch (mode) {
   case PICNIX_BOUNDARY_EMF: {
-    // remote: pack interior margins first (they are not modified by the local gather)
-    for (auto& p : a->peers) {
-      int nmsg = (int)p.send_chunk.size();
-      if (nmsg > 0) {
-        remote_halo_kernel<6, false, true><<<nmsg, HALO_THREADS, 0, a->stream>>>(
-            g, a->d.uf, p.d_send_desc, p.d_send_off[0], p.d_send[0], 0);
-        a->kernel_launches++;
-      }
+    // remote: pack interior margins first (they are not modified by the local gather); the messages of
+    // all peers in one launch
+    if (a->nmsg_send_all > 0) {
+      remote_halo_kernel<6, false, true><<<a->nmsg_send_all, HALO_THREADS, 0, a->stream>>>(
+          g, a->d.uf, a->d_send_desc_all, a->d_send_off_all[0], a->d_send_all[0], 0);
+      a->kernel_launches++;
     }
     field_halo_local_kernel<<<blocks, HALO_THREADS, 0, a->stream>>>(g, a->d);
     a->kernel_launches++;
@@ -682,13 +728,10 @@ int launch_halo_begin(picnix_arena* a, int mode)
   }
   case PICNIX_BOUNDARY_CUR: {
     // remote: pack ghost regions (read-only for the local gather as well)
-    for (auto& p : a->peers) {
-      int nmsg = (int)p.send_chunk.size();
-      if (nmsg > 0) {
-        remote_halo_kernel<4, true, true><<<nmsg, HALO_THREADS, 0, a->stream>>>(
-            g, a->d.uj, p.d_send_desc, p.d_send_off[1], p.d_send[1], 0);
-        a->kernel_launches++;
-      }
+    if (a->nmsg_send_all > 0) {
+      remote_halo_kernel<4, true, true><<<a->nmsg_send_all, HALO_THREADS, 0, a->stream>>>(
+          g, a->d.uj, a->d_send_desc_all, a->d_send_off_all[1], a->d_send_all[1], 0);
+      a->kernel_launches++;
     }
     current_halo_local_kernel<<<blocks, HALO_THREADS, 0, a->stream>>>(g, a->d);
     a->kernel_launches++;
@@ -725,8 +768,8 @@ int launch_halo_begin(picnix_arena* a, int mode)
       return status;
     if ((status = materialize_sort(a)) != PICNIX_OK)
       return status;
-    for (auto& p : a->peers)
-      PICNIX_CUDA(a, cudaMemsetAsync(p.d_psend_count, 0, sizeof(int), a->stream));
+    if (!a->peers.empty())
+      PICNIX_CUDA(a, cudaMemsetAsync(a->d_mig_counts, 0, a->peers.size() * 2 * sizeof(int), a->stream));
     // lagged-count protocol: bounds from the counts of the previous step (already on the host)
     if (a->mig_pending) {
       PICNIX_CUDA(a, cudaEventSynchronize(a->mig_event)); // recorded a step ago: no stall in steady state
@@ -785,8 +828,7 @@ int launch_halo_begin(picnix_arena* a, int mode)
       a->kernel_launches++;
       for (int i = 0; i < npeer; i++) {
         PeerPlan& p = a->peers[i];
-        PICNIX_CUDA(a, cudaMemcpyAsync(a->h_mig + 2 * i, p.d_psend_count, sizeof(int), cudaMemcpyDeviceToHost,
-                                       a->stream));
+        // (the counts travel to the host in one copy at the end of the exchange)
         p.psend_bytes = (p.send_bound + 1) * 8 * (int64_t)sizeof(double);
         p.precv_bytes = (p.recv_bound + 1) * 8 * (int64_t)sizeof(double);
       }
@@ -819,23 +861,17 @@ int launch_halo_end(picnix_arena* a, int mode)
   const Geom& g = a->g;
   switch (mode) {
   case PICNIX_BOUNDARY_EMF:
-    for (auto& p : a->peers) {
-      int nmsg = (int)p.recv_chunk.size();
-      if (nmsg > 0) {
-        remote_halo_kernel<6, false, false><<<nmsg, HALO_THREADS, 0, a->stream>>>(
-            g, a->d.uf, p.d_recv_desc, p.d_recv_off[0], p.d_recv[0], 0);
-        a->kernel_launches++;
-      }
+    if (a->nmsg_recv_all > 0) {
+      remote_halo_kernel<6, false, false><<<a->nmsg_recv_all, HALO_THREADS, 0, a->stream>>>(
+          g, a->d.uf, a->d_recv_desc_all, a->d_recv_off_all[0], a->d_recv_all[0], 0);
+      a->kernel_launches++;
     }
     break;
   case PICNIX_BOUNDARY_CUR:
-    for (auto& p : a->peers) {
-      int nmsg = (int)p.recv_chunk.size();
-      if (nmsg > 0) {
-        remote_halo_kernel<4, true, false><<<nmsg, HALO_THREADS, 0, a->stream>>>(
-            g, a->d.uj, p.d_recv_desc, p.d_recv_off[1], p.d_recv[1], 0);
-        a->kernel_launches++;
-      }
+    if (a->nmsg_recv_all > 0) {
+      remote_halo_kernel<4, true, false><<<a->nmsg_recv_all, HALO_THREADS, 0, a->stream>>>(
+          g, a->d.uj, a->d_recv_desc_all, a->d_recv_off_all[1], a->d_recv_all[1], 0);
+      a->kernel_launches++;
     }
     break;
   case PICNIX_BOUNDARY_MOM:
@@ -850,12 +886,20 @@ int launch_halo_end(picnix_arena* a, int mode)
     break;
   case PICNIX_BOUNDARY_PARTICLE: {
     if (a->mig_async_step) {
-      for (size_t i = 0; i < a->peers.size(); i++) {
-        PeerPlan& p = a->peers[i];
-        unpack_particle_bounded_kernel<<<148 * 2, HALO_THREADS, 0, a->stream>>>(g, a->d, p.d_precv, p.recv_bound,
-                                                                               p.d_rcount, a->chunk_begin);
+      const int npeer = (int)a->peers.size();
+      if (npeer > MAX_PEERS)
+        return fail(a, PICNIX_ERR_INVALID, "more than 32 peer ranks");
+      if (npeer > 0) {
+        PeerRecv pr;
+        for (int i = 0; i < npeer; i++) {
+          pr.recv[i]  = a->peers[i].d_precv;
+          pr.bound[i] = a->peers[i].recv_bound;
+        }
+        unpack_particle_all_kernel<<<dim3(148, npeer), HALO_THREADS, 0, a->stream>>>(g, a->d, pr, a->d_mig_counts,
+                                                                                    a->chunk_begin);
         a->kernel_launches++;
-        PICNIX_CUDA(a, cudaMemcpyAsync(a->h_mig + 2 * i + 1, p.d_rcount, sizeof(int), cudaMemcpyDeviceToHost,
+        // sent and received counts of all peers for the next step's bounds
+        PICNIX_CUDA(a, cudaMemcpyAsync(a->h_mig, a->d_mig_counts, npeer * 2 * sizeof(int), cudaMemcpyDeviceToHost,
                                        a->stream));
       }
       PICNIX_CUDA(a, cudaEventRecord(a->mig_event, a->stream));
