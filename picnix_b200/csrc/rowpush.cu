@@ -496,6 +496,7 @@ row_push_kernel(Geom g, DevPtrs d, RowConst rc, int c0, int cn, double delt)
     for (unsigned mk = om; mk != 0; mk &= mk - 1) {
       const int j = __ffs(mk) - 1;
       deposit_direct(ws->tile, ws->stg + j * REC, lm, run_index(ws->info[j]), half);
+      __syncwarp(); // the next record's window may overlap this one's: other lanes, same tile elements
     }
     if (FUSED)
       asm volatile("cp.async.wait_group 0;" ::: "memory");
