@@ -95,8 +95,13 @@ __global__ void segment_stat_kernel(DevPtrs d, int nseg)
     atomicMin(d.seg_stat + 0, minfree);
     atomicMax(d.seg_stat + 1, maxtail);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     d.seg_stat[2] = *d.spill_count;
+    // fatal device-side flags ride along (bit 0: spill list full, bit 2: foreign particle received,
+    // bit 3: far-mover list full), so a free-running host learns of them one step late without a
+    // synchronisation of its own
+    d.seg_stat[3] = (d.errflag[0] != 0 ? 1 : 0) | (d.errflag[2] != 0 ? 4 : 0) | (d.errflag[3] != 0 ? 8 : 0);
+  }
 }
 
 __global__ void reset_tail_kernel(DevPtrs d, int nseg)
@@ -192,6 +197,8 @@ int resolve_growth(picnix_arena* a)
     a->stat_spilled = a->h_stat[2];
     a->stat_pending = false;
     a->stat_known   = true;
+    if (a->h_stat[3] != 0) // the previous step raised a fatal flag: report it now (same texts as synchronize)
+      return picnix_cuda_synchronize(a);
   }
   const bool look = a->check_growth_always || !a->stat_known || a->stat_spilled > 0 ||
                     a->stat_minfree < 2 * a->stat_maxtail + 16;

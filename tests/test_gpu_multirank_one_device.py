@@ -195,3 +195,37 @@ def test_rebalance_moves_chunks_between_arenas():
             for isp in range(2):
                 assert s.get_np(ic, isp) == single.get_np(gid, isp)
                 assert np.array_equal(s.get_pindex(ic, isp), single.get_pindex(gid, isp))
+
+
+def test_foreign_particle_record_is_an_error():
+    """A received migration record whose destination chunk this rank does not own (a decomposition or
+    message-plan mismatch between ranks) must not vanish silently: errflag[2] -> PICNIX_ERR_INVALID at the
+    next synchronize, and one step late through the per-step statistics for a host that never synchronises."""
+    import torch
+
+    from picnix_b200 import CudaSim
+
+    ndims, cdims, nrank = (16, 16, 16), (2, 2, 2), 2
+    kw = dict(Ns=2, cc=10.0, delh=1.0, order=2)
+    boundary = capi.assign_initial(np.ones(8), nrank)
+    sims = [CudaSim(ndims, cdims, nrank=nrank, rank=r, boundary=boundary, **kw) for r in range(nrank)]
+    for s in sims:
+        s.set_option("async_migration", 0)
+        fill(s, ndims, cdims, problems.THERMAL_SPECIES, (8, 8), (5.0, 0.0, 0.0))
+    exchange_all(sims, MODE_EMF)
+    step_all(sims, 0.05)
+    for s in sims:
+        s.push_bfd(0.025)
+        s.push_deposit_fused(0.05)
+        s.boundary_begin(MODE_PARTICLE)
+    move_all(sims, MODE_PARTICLE)
+    # corrupt the destination chunk id of the first record rank 1 received (int32 at byte 56 of the record)
+    _, _, rp, rb = sims[1].comm_buffer(MODE_PARTICLE, 0)
+    assert rb >= 64
+    cuda_view(rp, rb)[56:60].copy_(torch.tensor(np.array([10 ** 6], dtype=np.int32).view(np.uint8)))
+    torch.cuda.synchronize()
+    sims[0].boundary_end(MODE_PARTICLE)
+    sims[1].boundary_end(MODE_PARTICLE)
+    sims[0].synchronize()
+    with pytest.raises(Exception, match="does not own"):
+        sims[1].synchronize()
