@@ -48,13 +48,13 @@ def test_headline_workload_is_the_survey_configuration():
 
 
 def test_ncu_capture_lookup_matches_workload_sizes():
-    for name in ("thermal3d", "cherenkov"):
+    for name in ("thermal3d", "cherenkov", "twostream"):
         wl = bench.Workload(name, args())
         ncell = int(np.prod(wl.dims))
         traffic, pipes = bench.ncu_traffic(ncell * sum(wl.ppc), ncell)
         alg = ncell * sum(wl.ppc) * bench.BYTES_PUSH_PER_PARTICLE + ncell * bench.BYTES_PUSH_PER_CELL
         assert traffic is not None and 1.0 <= traffic / alg < 1.1      # no wasted DRAM traffic
-        assert pipes["warps_per_sm"] in (8, 12)
+        assert pipes["warps_per_sm"] in (8, 12, 16)
     assert bench.ncu_traffic(12345, 678) == (None, None)
 
 
