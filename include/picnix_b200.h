@@ -113,13 +113,13 @@ int picnix_cuda_arena_destroy(picnix_arena_t* arena);
 const char* picnix_cuda_last_error(const picnix_arena_t* arena);
 
 /* tuning / testing switches:
- *   "force_generic" = 1  bypasses the tiled 3-D kernels (row-owner deposit): the thread-per-particle
+ *   "force_generic" = 1  bypasses the tiled kernels (3-D, 2-D, 1-D row-owner deposit): the thread-per-particle
  *                        kernels run instead
  *   "lazy_sort"     = 0  the counting sort always moves the particles (default 1: when the tiled
  *                        fused kernel will consume the result only the permutation is written and
  *                        the reordering rides on the next push; results are identical)
  *   "deposit_mma"   = 1  FP64-MMA formulation of the deposit (slower; kept as measured evidence)
- *   "row_kernel"    = 1  the round-1 tiled kernel (rowfused.cu) instead of rowpush.cu (default 2)
+ *   "row_kernel"    = 1  the round-1 tiled kernel (experiments/rowfused_v1.cu) instead of rowpush.cu (default 2)
  *   "check_growth"  = 1  look at the segment populations on the host before EVERY sort (default: only
  *                        when the previous step's statistics say a segment may fill up; see
  *                        picnix_cuda_get_growth_stats)
