@@ -152,6 +152,15 @@ public:
   {
   }
 
+  /// Physical boundaries of the problem.  An example whose MainChunk overrides set_boundary_field /
+  /// set_boundary_particle (example/mrx, example/shock) declares them here once instead, as boundary
+  /// kinds of the arena (picnix_cuda_set_boundary_condition); the device applies them after every halo
+  /// exchange and inside every position push.  Called on one chunk right after the arena is created.
+  virtual void declare_boundary_conditions(picnix_arena_t* arena)
+  {
+    (void)arena;
+  }
+
   virtual ~CudaPicChunk() override
   {
     Hub&                        hub = Hub::instance();
@@ -376,6 +385,7 @@ inline void ArenaHub::make_live()
   cfg.friedman     = c0->option.value("friedman", 0.0);
   cfg.buffer_ratio = c0->option.value("buffer_ratio", 0.2);
   check(picnix_cuda_arena_create(&cfg, nullptr, &arena), "arena_create");
+  c0->declare_boundary_conditions(arena);
 
   int32_t nchunk = 0, begin = 0;
   check(picnix_cuda_get_layout(arena, &nchunk, &begin, nullptr, nullptr, nullptr), "get_layout");

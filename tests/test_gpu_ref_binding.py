@@ -146,3 +146,98 @@ def test_reference_application_with_cuda_chunks(tmp_path, shape):
         assert np.array_equal(a[:, 6].view(np.int64), b[:, 6].view(np.int64))
         assert np.max(np.abs(a[:, :3] - b[:, :3])) < 1e-11 * 32
         assert np.max(np.abs(a[:, 3:6] - b[:, 3:6])) < 1e-11 * 10
+
+
+MRX_REF, MRX_CUDA = os.path.join(BUILD, "mrx_ref"), os.path.join(BUILD, "mrx_cuda")
+
+MRX_CONFIG = """
+[application]
+  basedir = 'data'
+  [application.log]
+    interval = 100
+  [application.rebalance]
+    interval = 1000000
+  [application.option]
+    vectorization = 'vector'
+    seed_type = 'fixed'
+    order = 2
+
+[[diagnostic]]
+  name = 'history'
+  interval = 1
+
+[[diagnostic]]
+  name = 'field'
+  interval = {nstep}
+
+[[diagnostic]]
+  name = 'particle'
+  interval = {nstep}
+  fraction = 1.0
+
+[parameter]
+  Nx = 64
+  Ny = 32
+  Nz = 1
+  Cx = 4
+  Cy = 2
+  Cz = 1
+  Ns = 2
+  delt = 0.1
+  delh = 0.2
+  lcs = 2.5
+  ncs = 8
+  nbg = 4
+  mime = 25
+  sigma = 0.0625
+  tite = 5.0
+  bg = 0.0
+  db = 0.1
+  phi = 0.0
+"""
+
+
+@pytest.mark.skipif(not (os.path.exists(MRX_REF) and os.path.exists(MRX_CUDA)),
+                    reason="host/ref_binding/_build/mrx_* not built")
+def test_mrx_application_with_cuda_chunks(tmp_path):
+    """BASELINE configs[3]: the reference's example/mrx application (Harris sheet between conducting walls,
+    MainChunk::setup with its own RNG, MainApplication with non-periodic y) unmodified on the CPU and with
+    its chunks on the B200 (host/ref_binding/mrx_cuda.cpp: the example's wall hooks replaced by
+    PICNIX_BC_CONDUCTING).  history, raw field dump and raw particle dump (as sets: the example assigns no
+    particle ids) must agree."""
+    nstep = 30
+    cfg = MRX_CONFIG.format(nstep=nstep)
+
+    def run(binary, workdir):
+        os.makedirs(workdir, exist_ok=True)
+        with open(os.path.join(workdir, "config.toml"), "w") as fp:
+            fp.write(cfg)
+        env = dict(os.environ, OMP_NUM_THREADS="4", PICNIX_SYNC_HOST_INTERVAL="1")
+        proc = subprocess.run([binary, "-c", "config.toml", "-t", str(0.1 * nstep)], cwd=workdir, env=env,
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert proc.returncode == 0, proc.stdout[-3000:]
+        return os.path.join(workdir, "data")
+
+    ref, gpu = run(MRX_REF, str(tmp_path / "ref")), run(MRX_CUDA, str(tmp_path / "gpu"))
+    ha, hb = read_history(gpu), read_history(ref)
+    assert ha.shape == hb.shape and ha.shape[0] >= nstep + 1
+    assert np.array_equal(ha[:, :2], hb[:, :2])
+    assert np.max(np.abs(ha[:, 2:4])) < 1e-10 and np.max(np.abs(hb[:, 2:4])) < 1e-10
+    scale = np.maximum(np.abs(hb[:, 4:]), 1e-3 * np.abs(hb[:, 4:]).max(axis=0))  # E^2/2 starts at zero
+    assert np.max(np.abs(ha[:, 4:] - hb[:, 4:]) / scale) < 1e-5                    # the printed precision
+
+    fa, fb = read_dump(gpu, "field", nstep), read_dump(ref, "field", nstep)
+    assert set(fa) == set(fb) and "uf" in fa
+    for name in fa:
+        assert fa[name].shape == fb[name].shape
+        assert np.max(np.abs(fa[name] - fb[name])) <= 1e-10 * np.max(np.abs(fb[name])), name
+
+    pa, pb = read_dump(gpu, "particle", nstep), read_dump(ref, "particle", nstep)
+    assert set(pa) == set(pb) and len(pa) >= 2
+    for name in pa:
+        a, b = pa[name].reshape(-1, 7), pb[name].reshape(-1, 7)
+        assert a.shape == b.shape and a.shape[0] > 0
+        a = a[np.lexsort(np.round(a[:, :6].T[::-1], 6))]
+        b = b[np.lexsort(np.round(b[:, :6].T[::-1], 6))]
+        assert np.max(np.abs(a[:, :3] - b[:, :3])) < 1e-10 * 12.8
+        assert np.max(np.abs(a[:, 3:6] - b[:, 3:6])) < 1e-10
