@@ -241,3 +241,176 @@ def test_mrx_application_with_cuda_chunks(tmp_path):
         b = b[np.lexsort(np.round(b[:, :6].T[::-1], 6))]
         assert np.max(np.abs(a[:, :3] - b[:, :3])) < 1e-10 * 12.8
         assert np.max(np.abs(a[:, 3:6] - b[:, 3:6])) < 1e-10
+
+
+TWOSTREAM_CONFIG = """
+# example/beam/twostream/config.toml as shipped (BASELINE configs[0]); two changes: seed_type = 'fixed'
+# (the default seeds every chunk from std::random_device, which no second run can reproduce) and no in-run
+# rebalancing (one rank; the binding moves chunks through picnix_cuda_chunk_pack/unpack between runs)
+[application]
+  basedir = 'data'
+  [application.log]
+    interval = 5000
+  [application.rebalance]
+    interval = 1000000
+  [application.option]
+    vectorization = 'vector'
+    seed_type = 'fixed'
+
+[[diagnostic]]
+  name = 'history'
+  interval = 10
+
+[[diagnostic]]
+  name = 'field'
+  interval = {nstep}
+
+[[diagnostic]]
+  name = 'particle'
+  interval = {nstep}
+  fraction = 1.0
+
+[parameter]
+  Nx = 512
+  Ny = 1
+  Nz = 1
+  Cx = 64
+  Cy = 1
+  Cz = 1
+  Ex = 0.0
+  Ey = 0.0
+  Ez = 0.0
+  Bx = 10.0
+  By = 0.0
+  Bz = 0.0
+  Ns = 3
+  cc = 50.0
+  delt = 0.01
+  delh = 1.0
+
+[[parameter.particle]]
+    np = 16
+    qm = -1.0
+    ro = 0.5
+    vt = 1.0
+    vx = 10.0
+    vy = 0.0
+    vz = 0.0
+
+[[parameter.particle]]
+    np = 16
+    qm = -1.0
+    ro = 0.5
+    vt = 1.0
+    vx = -10.0
+    vy = 0.0
+    vz = 0.0
+
+[[parameter.particle]]
+    np = 32
+    qm = +0.01
+    ro = 100.0
+    vt = 1.0
+    vx = 0.0
+    vy = 0.0
+    vz = 0.0
+"""
+
+CHERENKOV_CONFIG = """
+# example/cherenkov/config.toml as shipped (BASELINE configs[2]) with seed_type = 'fixed', no in-run
+# rebalancing and the diagnostics at the end of this short run
+[application]
+  basedir = 'data'
+  [application.log]
+    interval = 200
+  [application.option]
+    vectorization = 'vector'
+    seed_type = 'fixed'
+  [application.rebalance]
+    interval = 1000000
+
+[[diagnostic]]
+  interval = 5
+  name = 'history'
+
+[[diagnostic]]
+  interval = {nstep}
+  name = 'field'
+
+[[diagnostic]]
+  interval = {nstep}
+  name = 'particle'
+  fraction = 1.0
+
+[parameter]
+  Cx = 8
+  Cy = 8
+  Cz = 1
+  Ns = 2
+  Nx = 128
+  Ny = 128
+  Nz = 1
+  cc = 1.0
+  delh = 0.1
+  delt = 0.05
+  mime = 1
+  nppc = 32
+  phi = 0.0
+  sigma = 0.0
+  theta = 0.0
+  u0 = 0.1
+  vte = 0.1
+  vti = 0.1
+  wp = 1.0
+"""
+
+
+@pytest.mark.parametrize("app,config,dt,nstep,length", [("beam", TWOSTREAM_CONFIG, 0.01, 200, 512.0),
+                                                        ("cherenkov", CHERENKOV_CONFIG, 0.05, 40, 12.8)])
+def test_shipped_configurations_through_the_reference_application(tmp_path, app, config, dt, nstep, length):
+    """BASELINE configs[0] and [2] with the parameters the reference ships: the reference's application on
+    the CPU and the same application with CudaPicChunk on the B200 (1-D and 2-D tiled kernels, lazy sort,
+    halos, migration, moments for the history energies) agree on history, raw fields and raw particles."""
+    ref_bin, cuda_bin = os.path.join(BUILD, app + "_ref"), os.path.join(BUILD, app + "_cuda")
+    if not (os.path.exists(ref_bin) and os.path.exists(cuda_bin)):
+        pytest.skip("host/ref_binding/_build/%s_* not built" % app)
+    cfg = config.format(nstep=nstep)
+    out = {}
+    for tag, binary in (("ref", ref_bin), ("gpu", cuda_bin)):
+        workdir = str(tmp_path / tag)
+        os.makedirs(workdir, exist_ok=True)
+        with open(os.path.join(workdir, "config.toml"), "w") as fp:
+            fp.write(cfg)
+        env = dict(os.environ, OMP_NUM_THREADS="8", PICNIX_SYNC_HOST_INTERVAL="1")
+        proc = subprocess.run([binary, "-c", "config.toml", "-t", str(dt * nstep)], cwd=workdir, env=env,
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        assert proc.returncode == 0, proc.stdout[-3000:]
+        out[tag] = os.path.join(workdir, "data")
+    ha, hb = read_history(out["gpu"]), read_history(out["ref"])
+    assert ha.shape == hb.shape and ha.shape[0] >= 3
+    assert np.array_equal(ha[:, :2], hb[:, :2])
+    scale = np.maximum(np.abs(hb[:, 4:]), 1e-3 * np.abs(hb[:, 4:]).max(axis=0))
+    assert np.max(np.abs(ha[:, 4:] - hb[:, 4:]) / scale) < 1e-5      # the printed precision
+    # the Gauss residual is whatever the initial placement left; it must be the same number on both sides
+    assert np.max(np.abs(ha[:, 2:4] - hb[:, 2:4])) < 1e-9 * max(1.0, np.max(np.abs(hb[:, 2:4])))
+
+    fa, fb = read_dump(out["gpu"], "field", nstep), read_dump(out["ref"], "field", nstep)
+    assert set(fa) == set(fb) and "uf" in fa
+    for name in fa:
+        assert fa[name].shape == fb[name].shape
+        assert np.max(np.abs(fa[name] - fb[name])) <= 1e-9 * np.max(np.abs(fb[name])), name
+
+    pa, pb = read_dump(out["gpu"], "particle", nstep), read_dump(out["ref"], "particle", nstep)
+    assert set(pa) == set(pb) and len(pa) >= 2
+    for name in pa:
+        a, b = pa[name].reshape(-1, 7), pb[name].reshape(-1, 7)
+        assert a.shape == b.shape and a.shape[0] > 0
+        ida, idb = a[:, 6].view(np.int64), b[:, 6].view(np.int64)
+        if np.unique(idb).size == idb.size:                       # the example assigns ids: match by id
+            a, b = a[np.argsort(ida, kind="stable")], b[np.argsort(idb, kind="stable")]
+            assert np.array_equal(a[:, 6].view(np.int64), b[:, 6].view(np.int64))
+        else:                                                     # no ids: compare as sets
+            a = a[np.lexsort(np.round(a[:, :6].T[::-1], 6))]
+            b = b[np.lexsort(np.round(b[:, :6].T[::-1], 6))]
+        assert np.max(np.abs(a[:, :3] - b[:, :3])) < 1e-9 * length
+        assert np.max(np.abs(a[:, 3:6] - b[:, 3:6])) < 1e-8
