@@ -26,6 +26,9 @@ field halo, counting sort.  Weak scaling: every GPU owns its own 128^3 block of 
              (MEASURED_PEAKS.json), algorithmic bytes = 120 B/particle (R 56 + 4 B permutation + W 56
              + 4 B key) plus the field tile traffic per cell; `traffic` = DRAM bytes of one
              launch from the committed ncu capture.
+`application_loop` : (N=1, default workload) the reference's own application (unmodified example/thermal/main.cpp,
+             nix::Application::main) with its chunks bound to this library (host/ref_binding), same size, state
+             resident, timed by the application's log; tools/app_throughput.py.
 `cpu_baseline` / `--impl reference` : the UNMODIFIED reference (oracle/_ref, its own OpenMP loop
              over chunks and xsimd kernels) on all host cores, on a bounded sample of the workload.
 """
@@ -135,6 +138,7 @@ def parse_args():
     ap.add_argument("--ref-cells", type=int, default=0, help="cells per dimension of the CPU sample; 0: the workload's")
     ap.add_argument("--ref-steps", type=int, default=0, help="override steps of the reference arm")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed N>1 parity pre-check")
+    ap.add_argument("--no-app", action="store_true", help="skip the reference-application leg (N=1, thermal3d)")
     ap.add_argument("--parity-cells", type=int, default=0, help="cells per rank per dimension of the pre-check")
     return ap.parse_args()
 
@@ -537,6 +541,22 @@ def b200_main(args, rank, world):
         except Exception as exc:  # the reference binary is absent: say so instead of inventing a number
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {exc}"}
 
+    # the reference's OWN application loop (nix::Application::main + example/thermal/main.cpp, unmodified) with
+    # its chunks bound to this library, at the same size, timed by the application's log; extra evidence, not
+    # part of the contract keys, and never allowed to break the line
+    app = None
+    if rank == 0 and world == 1 and wl.name == "thermal3d" and not args.no_app and not args.no_cpu:
+        tool = os.path.join(ROOT, "tools", "app_throughput.py")
+        binary = os.path.join(ROOT, "host", "ref_binding", "_build", "thermal_cuda")
+        if os.path.exists(tool) and os.path.exists(binary):
+            try:
+                sim.close()
+                out = subprocess.run([sys.executable, tool, "--cells", str(wl.dims[0]), "--steps", "40"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=600)
+                app = json.loads(out.stdout.strip().split("\n")[-1])
+            except Exception as exc:
+                app = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
         line = {
             "metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -555,6 +575,7 @@ def b200_main(args, rank, world):
             "gpu_launches": int(launches1 - launches0),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "application_loop": app,
         }
         os.write(result_fd, (json.dumps(line) + "\n").encode())
 
