@@ -12,7 +12,9 @@ sys.path.insert(0, ROOT)
 from picnix_b200 import CudaSim, problems  # noqa: E402
 
 CASES = [
-    # name, cells, species, ppc per species, cc, dt, B0
+    # name, cells, species, ppc per species, cc, dt, B0[, chunk edge]
+    ("thermal ppc=2x32, chunks 8^3", 128, problems.THERMAL_SPECIES, (32, 32), 10.0, 0.05, (5.0, 0, 0), 8),
+    ("thermal ppc=2x32, chunks 32^3", 128, problems.THERMAL_SPECIES, (32, 32), 10.0, 0.05, (5.0, 0, 0), 32),
     ("thermal ppc=2x8", 128, problems.THERMAL_SPECIES, (8, 8), 10.0, 0.05, (5.0, 0, 0)),
     ("thermal ppc=2x16", 128, problems.THERMAL_SPECIES, (16, 16), 10.0, 0.05, (5.0, 0, 0)),
     ("thermal ppc=2x32 (headline)", 128, problems.THERMAL_SPECIES, (32, 32), 10.0, 0.05, (5.0, 0, 0)),
@@ -22,9 +24,11 @@ CASES = [
 steps, warmup = 10, 3
 stream = torch.cuda.Stream()
 print(f"{'case':36s} {'particles':>12s} {'ms/step':>9s} {'particle-steps/s':>18s} {'leaving/step':>13s}")
-for name, cells, species, ppc, cc, dt, B0 in CASES:
+for case in CASES:
+    name, cells, species, ppc, cc, dt, B0 = case[:7]
+    edge = case[7] if len(case) > 7 else 16
     nd = (cells,) * 3
-    cd = tuple(n // 16 for n in nd)
+    cd = tuple(n // edge for n in nd)
     sim = CudaSim(nd, cd, Ns=len(species), cc=cc, delh=1.0, order=2)
     sim.set_stream(stream.cuda_stream)
     problems.setup_uniform_plasma(sim, nd, cd, species, ppc, B0=B0, seed=1)
