@@ -133,8 +133,10 @@ struct MomentTile {
 
 template <int Dim, int Order>
 __global__ void __launch_bounds__(MTHREADS)
-moment_row_kernel(Geom g, DevPtrs d)
+moment_row_kernel(Geom g, DevPtrs d, const int* __restrict__ perm)
 {
+  // perm != nullptr: a lazy sort is pending -- sorted slot j of a segment still sits in slot perm[j] of xu
+  // (sort.cu); the particles are fetched through it instead of being physically reordered first
   using T = MomentTile<Dim, Order>;
   constexpr int N = T::N, NY = T::NY, NZ = T::NZ, NPTS = T::NPTS, XT = T::XT, TILE = T::TILE, REC = T::REC;
   extern __shared__ double msm[];
@@ -187,7 +189,7 @@ moment_row_kernel(Geom g, DevPtrs d)
   auto   fetch = [&](int cell, int b0) {
     const int pe = __shfl_sync(0xffffffffu, pcut, cell + 1);
     if (b0 + lane < pe) {
-      const int64_t i = off + b0 + lane;
+      const int64_t i = perm != nullptr ? off + perm[off + b0 + lane] : off + b0 + lane;
 #pragma unroll
       for (int k = 0; k < 6; k++)
         nx[k] = d.xu[k * d.pcap + i];
@@ -368,7 +370,8 @@ void launch_moment_kernels(picnix_arena* a)
     const int     nrun  = (g.dims[2] + MRUN - 1) / MRUN;
     const int64_t warps = (int64_t)a->nseg * (Dim >= 3 ? g.dims[0] : 1) * (Dim >= 2 ? g.dims[1] : 1) * nrun;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::BYTES);
-    kern<<<(unsigned)((warps + MWARPS - 1) / MWARPS), MTHREADS, T::BYTES, a->stream>>>(g, a->d);
+    kern<<<(unsigned)((warps + MWARPS - 1) / MWARPS), MTHREADS, T::BYTES, a->stream>>>(
+        g, a->d, a->perm_pending ? a->d.perm : nullptr);
   } else {
     int maxcap = 0;
     for (int s = 0; s < a->nseg; s++)
@@ -418,9 +421,13 @@ int launch_deposit_moment(picnix_arena* a)
   int status = ensure_moment_array(a);
   if (status != PICNIX_OK)
     return status;
-  if ((status = materialize_sort(a)) != PICNIX_OK)
-    return status;
   const Geom& g = a->g;
+  // the row-tile kernel reads through a pending lazy-sort permutation; everything else wants ordered arrays
+  const int  npts     = g.dimension == 3 ? (g.order + 1) * (g.order + 1) * (g.order + 1)
+                                          : (g.dimension == 2 ? (g.order + 1) * (g.order + 1) : g.order + 1);
+  const bool row_path = a->pindex_valid && g.order % 2 == 0 && npts <= 32 && !a->force_generic;
+  if (!row_path && (status = materialize_sort(a)) != PICNIX_OK)
+    return status;
   // fill_all(um, 0), pic/engine/moment.hpp:104,166
   PICNIX_CUDA(a, cudaMemsetAsync(a->d.um, 0, (size_t)g.nchunk * g.Ng * g.Ns * NMOM * sizeof(double),
                                  a->stream));
