@@ -100,6 +100,27 @@ def test_tiled_kernel_variants_relativistic_multistep(pusher, interp):
     assert same and dx < 1e-11 and du < 1e-10
 
 
+@pytest.mark.parametrize("nspecies", [3, 4, 5])
+def test_tiled_3d_kernel_several_species(nspecies):
+    """The merged particle stream of the 3-D tiled kernel holds up to four species (the entry table then
+    fills all 32 lanes); five fall back to the round-1 kernel.  Drifting beams (the 3-D variant of
+    example/beam/twostream) plus extra species, ragged and empty segments, several steps."""
+    species = (problems.TWOSTREAM_SPECIES + [dict(qm=+0.5, ro=1.0, vt=0.7, drift=(0.0, 3.0, -2.0)),
+                                             dict(qm=-0.2, ro=2.0, vt=0.4, drift=(1.0, 0.0, 4.0))])[:nspecies]
+    ppc = (6, 5, 9, 4, 3)[:nspecies]
+    thin = lambda ic, isp, n: 0 if (ic == 3 and isp == 1) else (n if (ic + isp) % 3 else n // 2)
+    ref, gpu = make_pair((16, 16, 32), (2, 2, 2), species, ppc, 50.0, B0=(10.0, 2.0, 0.0), thin=thin)
+    dt = 0.01
+    ref.step(dt, 10)
+    gpu.step(dt, 10)
+    gpu.synchronize()
+    assert counts_equal(gpu, ref)
+    assert field_err(gpu, ref, FIELD_UF) < 1e-10
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-10
+    dx, du, same = particle_err(gpu, ref, scale_x=32.0, scale_u=50.0)
+    assert same and dx < 1e-11 and du < 1e-10
+
+
 def test_tiled_2d_kernel_far_movers_and_phases():
     """The 2-D tiled kernel (rowpush2d.cu): one fused push + deposit against the reference's separate
     calls, with a time step so large that many particles cross more than one cell (far-mover list)."""
