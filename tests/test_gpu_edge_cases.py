@@ -121,6 +121,26 @@ def test_tiled_3d_kernel_several_species(nspecies):
     assert same and dx < 1e-11 and du < 1e-10
 
 
+@pytest.mark.parametrize("ndims,cdims", [((12, 24, 48), (2, 2, 2)),     # chunk 6 x 12 x 24: 3 x-segments, 3 y-groups
+                                         ((1, 40, 80), (1, 2, 2)),      # chunk 20 x 40: 5 x-segments, 5 y-groups
+                                         ((1, 1, 72), (1, 1, 3)),       # chunk 24: 3 segments per chunk, 9 in all
+                                         ((10, 12, 24), (2, 2, 2)),     # chunk x = 12: not a multiple of 8 -> generic
+                                         ((1, 18, 32), (1, 3, 2))])     # chunk y = 6: not a multiple of 4 -> generic
+def test_chunk_shapes_of_the_tiled_kernels(ndims, cdims):
+    """Row geometry of the tiled kernels away from the cubic benchmark chunk: several x-segments and y-groups
+    per chunk in every dimensionality, and shapes that do not split (thread-per-particle path)."""
+    ref, gpu = make_pair(ndims, cdims, problems.THERMAL_SPECIES, (6, 6), 10.0, B0=(5.0, 1.0, 0.5))
+    scale = float(max(ndims))
+    ref.step(0.05, 8)
+    gpu.step(0.05, 8)
+    gpu.synchronize()
+    assert counts_equal(gpu, ref)
+    assert field_err(gpu, ref, FIELD_UF) < 1e-10
+    assert field_err(gpu, ref, FIELD_UJ) < 1e-10
+    dx, du, same = particle_err(gpu, ref, scale_x=scale, scale_u=10.0)
+    assert same and dx < 1e-11 and du < 1e-10
+
+
 def test_tiled_2d_kernel_far_movers_and_phases():
     """The 2-D tiled kernel (rowpush2d.cu): one fused push + deposit against the reference's separate
     calls, with a time step so large that many particles cross more than one cell (far-mover list)."""
