@@ -94,7 +94,7 @@ def step_all(sims, dt):
 
 @pytest.mark.parametrize("async_migration", [0, 1])
 @pytest.mark.parametrize("ndims,cdims,nrank", [((1, 32, 32), (1, 4, 4), 3), ((16, 16, 16), (2, 2, 2), 2),
-                                               ((16, 32, 16), (2, 4, 2), 4)])
+                                               ((16, 32, 16), (2, 4, 2), 4), ((1, 1, 128), (1, 1, 16), 3)])
 def test_ranks_on_one_device_equal_single_arena(ndims, cdims, nrank, async_migration):
     from picnix_b200 import CudaSim
 
@@ -229,3 +229,45 @@ def test_foreign_particle_record_is_an_error():
     sims[0].synchronize()
     with pytest.raises(Exception, match="does not own"):
         sims[1].synchronize()
+
+
+def test_conducting_walls_across_ranks_equal_single_arena():
+    """Physical boundary kinds in a multi-rank run: the mrx geometry (periodic x, conducting walls in y) split
+    over three ranks equals the single-arena run (which tests/test_gpu_boundaries.py pins against the example)."""
+    from picnix_b200 import CudaSim
+
+    ndims, cdims, nrank = (1, 32, 32), (1, 4, 4), 3
+    species, ppc, B0, dt, nstep = problems.THERMAL_SPECIES, (8, 8), (5.0, 0.0, 1.0), 0.05, 12
+    kw = dict(Ns=2, cc=10.0, delh=1.0, order=2, periodic=(1, 0, 1))
+
+    def walls(sim):
+        for side in (0, 1):
+            sim.set_boundary_condition(1, side, capi.BC_CONDUCTING)
+
+    single = CudaSim(ndims, cdims, **kw)
+    walls(single)
+    fill(single, ndims, cdims, species, ppc, B0)
+    single.exchange(MODE_EMF)
+    boundary = capi.assign_initial(single.get_np_all().sum(axis=1).astype(np.float64), nrank)
+    sims = [CudaSim(ndims, cdims, nrank=nrank, rank=r, boundary=boundary, **kw) for r in range(nrank)]
+    for s in sims:
+        walls(s)
+        s.set_option("async_migration", 1)
+        fill(s, ndims, cdims, species, ppc, B0)
+    exchange_all(sims, MODE_EMF)
+    n0 = sum(int(s.get_np_all().sum()) for s in sims)
+    single.step(dt, nstep)
+    single.synchronize()
+    for _ in range(nstep):
+        step_all(sims, dt)
+    assert sum(int(s.get_np_all().sum()) for s in sims) == n0      # the walls reflect: nobody leaves
+    for s in sims:
+        s.synchronize()
+        for ic in range(s.nchunk):
+            gid = s.chunk_id_begin + ic
+            for which in (0, 1):
+                a, b = s.get_field(ic, which), single.get_field(gid, which)
+                assert np.max(np.abs(a - b)) <= 1e-11 * max(np.max(np.abs(b)), 1e-300), (gid, which)
+            for isp in range(2):
+                assert s.get_np(ic, isp) == single.get_np(gid, isp)
+                assert np.array_equal(s.get_pindex(ic, isp), single.get_pindex(gid, isp))
